@@ -1,0 +1,13 @@
+"""pytest configuration: registers the `gpu` marker and puts the in-tree
+package (src layout: d-vqvae_b200/dvq) and the repo root on sys.path."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "d-vqvae_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
