@@ -1,0 +1,91 @@
+// Shared internals of libdvq_sm100.so (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "dvq.h"
+
+namespace dvq {
+
+// thread-local last-error text behind dvq_last_error()
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define DVQ_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return ::dvq::fail(DVQ_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                         __FILE__, __LINE__);                                             \
+  } while (0)
+
+struct DeviceProps {
+  int sm_count;
+  int cc_major;
+  int cc_minor;
+  int max_smem_optin;
+};
+int device_props(DeviceProps* out);  // cached per device
+
+// instrumentation (dvq_api.cu)
+void count_launch(int n = 1);
+void profile_mark(int stage, bool begin, cudaStream_t s);  // no-op unless dvq_profile_enable(1)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- workspace layout of dvq_vq_forward (all offsets 256-byte aligned) -------------------
+struct VqWorkspace {
+  size_t off_ee;        // float [K]            ||e_k||^2
+  size_t off_counters;  // int   [8]            refine-list length, overflow flags
+  size_t off_rowlist;   // int   [N]            rows the tensor-core filter could not decide
+  size_t off_bop;       // operand image of the codebook for the tcgen05 path
+  size_t off_rowmeta;   // float [N]            (reserved)
+  size_t total;
+};
+VqWorkspace vq_workspace_layout(int64_t N, int K, int D, int flags);
+
+// ---- kernels launched by the API layer ---------------------------------------------------
+// ee[k] = sum_d E[k,d]^2
+int launch_code_norms(const float* E, int K, int D, float* ee, cudaStream_t s);
+
+// Exact FP32 CUDA-core path.  row_list == nullptr: rows [0,N).  Otherwise rows
+// row_list[0 .. *n_list) (device-side count), used as the refine stage of the tcgen05 path.
+int launch_vq_simt(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
+                   float* z_q, int64_t* idx, unsigned long long* hist, double* sse,
+                   const int* row_list, const int* n_list, cudaStream_t s);
+
+// tcgen05 filter kernel (vq_tc_sm100.cu); supported(K,D) says whether the shape is handled.
+bool vq_tc_supported(int64_t N, int K, int D);
+size_t vq_tc_operand_bytes(int K, int D);
+int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
+                 float* z_q, int64_t* idx, unsigned long long* hist, double* sse,
+                 void* bop, int* counters, int* row_list, cudaStream_t s);
+
+int launch_onehot(const int64_t* idx, int64_t N, int K, float* onehot, cudaStream_t s);
+int launch_finalize(const unsigned long long* hist, const double* sse, int64_t N, int K, int D, float al,
+                    float beta, float* loss, float* ppl, cudaStream_t s);
+int launch_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, float* out, int* oob,
+                  cudaStream_t s);
+
+// PointNet
+size_t pointnet_workspace_bytes(int B, int C, int P);
+int launch_pointnet(const float* x, const DvqPointNetWeights* w, int B, int C, int P, float* feat,
+                    float* trans, void* ws, size_t ws_bytes, cudaStream_t s);
+
+// ---- small device helpers ----------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace dvq

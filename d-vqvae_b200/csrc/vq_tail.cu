@@ -1,0 +1,125 @@
+// HBM-bound tail kernels of the VQ path: optional one-hot materialisation
+// (quantizer.py:40-42), the scalar finalisation of loss / perplexity (:56-57, :63-64) and the
+// index -> embedding gather behind get_emb (:68-75).
+#include "dvq_common.cuh"
+
+namespace dvq {
+namespace {
+
+// min_encodings [N,K] fp32: every element written exactly once with coalesced 128-bit stores
+// (algorithmic bytes: 4*N*K written + 8*N read).
+__global__ void onehot_kernel_v4(const int64_t* __restrict__ idx, int64_t N, int K, float* __restrict__ out) {
+  const int kv = K >> 2;
+  const int64_t total = N * (int64_t)kv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / kv;
+    const int col = (int)(i - row * kv) << 2;
+    const int k = (int)__ldg(idx + row);
+    float4 v;
+    v.x = (col + 0 == k) ? 1.f : 0.f;
+    v.y = (col + 1 == k) ? 1.f : 0.f;
+    v.z = (col + 2 == k) ? 1.f : 0.f;
+    v.w = (col + 3 == k) ? 1.f : 0.f;
+    __stcs(reinterpret_cast<float4*>(out) + i, v);  // streaming store: never re-read
+  }
+}
+__global__ void onehot_kernel_s(const int64_t* __restrict__ idx, int64_t N, int K, float* __restrict__ out) {
+  const int64_t total = N * (int64_t)K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / K;
+    const int col = (int)(i - row * K);
+    out[i] = (col == (int)__ldg(idx + row)) ? 1.f : 0.f;
+  }
+}
+
+__global__ void finalize_kernel(const unsigned long long* __restrict__ hist, const double* __restrict__ sse,
+                                int64_t N, int K, int D, float al, float beta, float* __restrict__ loss,
+                                float* __restrict__ ppl) {
+  __shared__ double red[32];
+  double s = 0.0;
+  const double inv_n = 1.0 / (double)N;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const double p = (double)hist[k] * inv_n;
+    s += p * log(p + 1e-10);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    *ppl = (float)exp(-t);
+    const float m = (float)(*sse / ((double)N * (double)D));
+    *loss = __fadd_rn(__fmul_rn(al, m), __fmul_rn(beta, m));
+  }
+}
+
+// out[n,:] = E[idx[n],:]; half-warp or full-warp per row depending on D, 128-bit accesses.
+template <bool VEC>
+__global__ void gather_kernel(const float* __restrict__ E, const int64_t* __restrict__ idx, int64_t N, int K,
+                              int D, float* __restrict__ out, int* __restrict__ oob) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < N; row += nwarps) {
+    const int64_t k = __ldg(idx + row);
+    const bool ok = (k >= 0 && k < K);
+    if (!ok && lane == 0 && oob) atomicExch(oob, 1);
+    const float* src = E + (ok ? k : 0) * (int64_t)D;
+    float* dst = out + row * (int64_t)D;
+    if (VEC) {
+      for (int c = lane * 4; c < D; c += 128) {
+        float4 v = ok ? ldg4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(dst + c) = v;
+      }
+    } else {
+      for (int c = lane; c < D; c += 32) dst[c] = ok ? __ldg(src + c) : 0.f;
+    }
+  }
+}
+}  // namespace
+
+int launch_onehot(const int64_t* idx, int64_t N, int K, float* onehot, cudaStream_t s) {
+  if (N == 0) return DVQ_OK;
+  DeviceProps dp;
+  int rc = device_props(&dp);
+  if (rc) return rc;
+  const int threads = 256;
+  const int blocks = dp.sm_count * 8;
+  if (K % 4 == 0 && reinterpret_cast<uintptr_t>(onehot) % 16 == 0)
+    onehot_kernel_v4<<<blocks, threads, 0, s>>>(idx, N, K, onehot);
+  else
+    onehot_kernel_s<<<blocks, threads, 0, s>>>(idx, N, K, onehot);
+  DVQ_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return DVQ_OK;
+}
+
+int launch_finalize(const unsigned long long* hist, const double* sse, int64_t N, int K, int D, float al,
+                    float beta, float* loss, float* ppl, cudaStream_t s) {
+  finalize_kernel<<<1, 256, 0, s>>>(hist, sse, N, K, D, al, beta, loss, ppl);
+  DVQ_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return DVQ_OK;
+}
+
+int launch_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, float* out, int* oob,
+                  cudaStream_t s) {
+  if (N == 0) return DVQ_OK;
+  DeviceProps dp;
+  int rc = device_props(&dp);
+  if (rc) return rc;
+  const int threads = 256;
+  int64_t blocks = (N * 32 + threads - 1) / threads;
+  if (blocks > (int64_t)dp.sm_count * 16) blocks = (int64_t)dp.sm_count * 16;
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(E) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  if (vec)
+    gather_kernel<true><<<(unsigned)blocks, threads, 0, s>>>(E, idx, N, K, D, out, oob);
+  else
+    gather_kernel<false><<<(unsigned)blocks, threads, 0, s>>>(E, idx, N, K, D, out, oob);
+  DVQ_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return DVQ_OK;
+}
+
+}  // namespace dvq

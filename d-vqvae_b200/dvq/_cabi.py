@@ -1,0 +1,111 @@
+"""ctypes binding of libdvq_sm100.so (C ABI declared in include/dvq.h).
+
+There is deliberately no fallback: if the shared library has not been built
+(``python d-vqvae_b200/build.py``) importing this module raises, and every
+compute call on a machine without an sm_100 GPU raises ``RuntimeError`` with the
+library's own message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdvq_sm100.so")
+
+ABI_VERSION = 1
+DVQ_TRAIN = 0x1
+DVQ_WRITE_ONEHOT = 0x2
+DVQ_PATH_AUTO = 0x00
+DVQ_PATH_SIMT = 0x10
+DVQ_PATH_TC = 0x20
+
+STATUS_NAMES = {0: "DVQ_OK", -1: "DVQ_ERR_BAD_SHAPE", -2: "DVQ_ERR_BAD_ALIGN", -3: "DVQ_ERR_UNSUPPORTED_ARCH",
+                -4: "DVQ_ERR_WORKSPACE", -5: "DVQ_ERR_CUDA", -6: "DVQ_ERR_NCCL", -7: "DVQ_ERR_BAD_ARG"}
+
+# every symbol include/dvq.h declares: name -> (restype, argtypes)
+_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+SYMBOLS = {
+    "dvq_abi_version": (_i, []),
+    "dvq_last_error": (C.c_char_p, []),
+    "dvq_launch_count": (C.c_longlong, []),
+    "dvq_profile_enable": (_i, [_i]),
+    "dvq_profile_mean": (_i, [C.POINTER(_f), C.POINTER(_i), _i]),
+    "dvq_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "dvq_vq_workspace_bytes": (_i, [_i64, _i, _i, _i, C.POINTER(_sz)]),
+    "dvq_vq_forward": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dvq_vq_finalize": (_i, [_vp, _vp, _i64, _i, _i, _f, _f, _vp, _vp, _vp]),
+    "dvq_gather": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "dvq_onehot": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "dvq_host_ctx_create": (_i, [_i64, _i, _i, C.POINTER(_vp)]),
+    "dvq_host_ctx_destroy": (_i, [_vp]),
+    "dvq_vq_forward_host": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, C.POINTER(_f), C.POINTER(_f)]),
+    "dvq_pointnet_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "dvq_pointnet_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "dvq_allreduce_stats": (_i, [_vp, _vp, _vp, _i, _vp]),
+}
+
+
+class PointNetWeights(C.Structure):
+    """Mirror of ``DvqPointNetWeights`` (include/dvq.h): device pointers to BN-folded fp32 weights."""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "stn_w1", "stn_b1", "stn_w2", "stn_b2", "stn_w3", "stn_b3",
+        "stn_fc1_w", "stn_fc1_b", "stn_fc2_w", "stn_fc2_b", "stn_fc3_w", "stn_fc3_b",
+        "w1", "b1", "w2", "b2", "w3", "b3")]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "dvq: %s is missing — build it with `python d-vqvae_b200/build.py` "
+        "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SYMBOLS.items():
+    _fn = getattr(lib, _name)  # AttributeError here == header and library disagree
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if lib.dvq_abi_version() != ABI_VERSION:
+    raise ImportError("dvq: ABI mismatch: library %d, binding %d" % (lib.dvq_abi_version(), ABI_VERSION))
+
+
+def last_error() -> str:
+    msg = lib.dvq_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str = "") -> None:
+    """Raise ``RuntimeError(dvq_last_error())`` on any non-zero return (SURVEY §8b error convention)."""
+    if rc != 0:
+        raise RuntimeError("%s%s: %s" % (what + ": " if what else "", STATUS_NAMES.get(rc, str(rc)), last_error()))
+
+
+def device_info():
+    sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+    check(lib.dvq_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "dvq_device_info")
+    return sm.value, maj.value, mnr.value
+
+
+def vq_workspace_bytes(n: int, k: int, d: int, flags: int) -> int:
+    out = C.c_size_t()
+    check(lib.dvq_vq_workspace_bytes(n, k, d, flags, C.byref(out)), "dvq_vq_workspace_bytes")
+    return out.value
+
+
+def pointnet_workspace_bytes(b: int, c: int, p: int) -> int:
+    out = C.c_size_t()
+    check(lib.dvq_pointnet_workspace_bytes(b, c, p, C.byref(out)), "dvq_pointnet_workspace_bytes")
+    return out.value
+
+
+def launch_count() -> int:
+    return int(lib.dvq_launch_count())
+
+
+def profile_mean():
+    """Mean CUDA-event time (ms) per stage of the dvq_vq_forward calls since dvq_profile_enable(1):
+    ((code_norms, main_kernel, refine, onehot), calls_averaged)."""
+    buf = (C.c_float * 4)()
+    cnt = (C.c_int * 4)()
+    check(lib.dvq_profile_mean(buf, cnt, 4), "dvq_profile_mean")
+    return tuple(float(v) for v in buf), tuple(int(v) for v in cnt)

@@ -1,0 +1,72 @@
+"""Multi-GPU plumbing of the VQ path: rows sharded by rank, codebook replicated,
+ONE exchange step — the sum over ranks of the usage histogram ``hist[K]`` (uint64) and the
+squared-error sum ``sse`` (float64) — between ``dvq_vq_forward`` and ``dvq_vq_finalize``.
+The integer histogram makes perplexity independent of the number of ranks exactly; the loss
+differs only by fp64 summation order.  The inference path and PointNet need no collective.
+
+One process per GPU, launched by torchrun; ``torch.distributed`` provides rendezvous and the
+communicator.  On CUDA tensors with the NCCL backend the reduction goes through the C ABI
+(``dvq_allreduce_stats``: both buffers in one NCCL group on the current stream, using torch's
+own ``ncclComm_t``); any other backend (gloo in the CPU tests) uses ``all_reduce`` directly.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as tdist
+
+
+def shard_bounds(n_rows: int, rank: int, world: int):
+    """Contiguous row block [lo, hi) of rank ``rank``: sizes differ by at most one row."""
+    base, rem = divmod(int(n_rows), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _nccl_comm_ptr(group, device):
+    try:
+        backend = group._get_backend(torch.device(device))
+        ptr = backend._comm_ptr()
+        return int(ptr) if ptr else None
+    except Exception:
+        return None
+
+
+def allreduce_stats(stats: torch.Tensor, n_e: int, n_local: int, group=None) -> int:
+    """In-place sum over ranks of ``stats = [hist (n_e x int64 bit-pattern of uint64) | sse (float64 bits)]``.
+    Returns the global row count (sum of ``n_local``)."""
+    if group is None:
+        group = tdist.group.WORLD
+    world = tdist.get_world_size(group)
+    if world == 1:
+        return int(n_local)
+    hist = stats[:n_e]
+    sse = stats[n_e:n_e + 1].view(torch.float64)
+    done = False
+    if stats.is_cuda and tdist.get_backend(group) == "nccl":
+        comm = _nccl_comm_ptr(group, stats.device)
+        if comm is not None:
+            from . import _cabi
+            with torch.cuda.device(stats.device):
+                _cabi.check(_cabi.lib.dvq_allreduce_stats(
+                    comm, hist.data_ptr(), sse.data_ptr(), n_e,
+                    torch.cuda.current_stream(stats.device).cuda_stream), "dvq_allreduce_stats")
+            done = True
+    if not done:
+        tdist.all_reduce(hist, op=tdist.ReduceOp.SUM, group=group)
+        tdist.all_reduce(sse, op=tdist.ReduceOp.SUM, group=group)
+    # global row count: the histogram sums to it, so no second message is needed when every
+    # row was counted; ranks may hold different shard sizes
+    n = torch.tensor([int(n_local)], dtype=torch.int64, device=stats.device)
+    tdist.all_reduce(n, op=tdist.ReduceOp.SUM, group=group)
+    return int(n.item())
+
+
+def shard_module(module, group=None):
+    """Mark every ``dvq.VectorQuantizer`` under ``module`` as row-sharded over ``group``."""
+    from .quantizer import VectorQuantizer
+    if group is None:
+        group = tdist.group.WORLD
+    for m in module.modules():
+        if isinstance(m, VectorQuantizer):
+            m.process_group = group
+    return module

@@ -1,0 +1,211 @@
+"""``VectorQuantizer`` — drop-in for the reference's ``network/vqvae/quantizer.py:10-75``.
+
+Same constructor ``(n_e, e_dim, beta, al)`` (:20), same parameter key
+``embedding.weight`` ``[n_e, e_dim]`` with the ``U(-1/n_e, 1/n_e)`` init (:26-27), same
+return order — train path ``(loss, z_q, perplexity, min_encodings, min_encoding_indices)``
+(:67), inference path ``(min_encoding_indices, z_q)`` (:54) — and ``get_emb(idx, dim)`` (:68).
+Everything between is one call into the C ABI (``dvq_vq_forward`` + ``dvq_vq_finalize``):
+the N x K distance matrix, the host-built one-hot and the second GEMM of the reference do not
+exist here.  There is no CPU path: inputs must be fp32 CUDA tensors.
+
+Differences that are deliberate and documented:
+* ``min_encodings`` ([N,K] fp32 one-hot, 1 TiB at BASELINE config 4) is materialised only while
+  it is at most ``onehot_limit_bytes`` (default 2 GiB); above that the 5-tuple carries a
+  ``LazyOneHot`` that can still produce it on demand.  Both reference callers discard it
+  (network/VQVAE.py:32).
+* ``get_emb`` accepts a batch of indices (the reference's scatter/view is valid for B=1 only);
+  for one index the result is identical.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from . import dist as _dist
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class LazyOneHot:
+    """Stand-in for ``min_encodings`` when N*K*4 bytes would be unreasonable to allocate."""
+
+    def __init__(self, indices: torch.Tensor, n_e: int):
+        self.indices = indices
+        self.n_e = n_e
+        self.shape = torch.Size((indices.shape[0], n_e))
+        self.dtype = torch.float32
+        self.device = indices.device
+
+    def materialize(self) -> torch.Tensor:
+        out = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+        _onehot_into(self.indices, self.n_e, out)
+        return out
+
+    def __repr__(self):
+        return "LazyOneHot(shape=%s, device=%s)" % (tuple(self.shape), self.device)
+
+
+def _onehot_into(indices: torch.Tensor, n_e: int, out: torch.Tensor) -> None:
+    """quantizer.py:40-42 through ``dvq_onehot`` (one coalesced write pass, no memset+scatter)."""
+    with torch.cuda.device(out.device):
+        _cabi.check(_cabi.lib.dvq_onehot(indices.data_ptr(), indices.shape[0], n_e, out.data_ptr(),
+                                         _stream_ptr(out.device)), "dvq_onehot")
+
+
+class _VQFunction(torch.autograd.Function):
+    """Autograd wrapper of the fused forward.  Backward of
+    ``loss = al*mean((sg[z_q]-z)^2) + beta*mean((z_q-sg[z])^2)`` and of the straight-through
+    ``z + sg[z_q - z]`` (quantizer.py:56-60):
+        dz = g_zq + g_loss * al   * 2 (z - e) / (N*D)
+        dE[k] = sum_{n: idx_n = k} g_loss * beta * 2 (e - z) / (N*D)."""
+
+    @staticmethod
+    def forward(ctx, z, weight, module):
+        loss, z_q, ppl, idx = module._forward_train_raw(z, weight)
+        ctx.save_for_backward(z, weight, idx)
+        ctx.al, ctx.beta = float(module.al), float(module.beta)
+        ctx.mark_non_differentiable(ppl, idx)
+        return loss, z_q, ppl, idx
+
+    @staticmethod
+    def backward(ctx, g_loss, g_zq, _g_ppl, _g_idx):
+        z, weight, idx = ctx.saved_tensors
+        flat = z.reshape(-1, weight.shape[1])
+        e = weight.index_select(0, idx.view(-1))
+        scale = 2.0 / flat.numel()
+        diff = (flat - e) * scale
+        gz = gw = None
+        if ctx.needs_input_grad[0]:
+            gz = (g_loss * ctx.al) * diff
+            if g_zq is not None:
+                gz = gz + g_zq.reshape_as(flat)
+            gz = gz.view_as(z)
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros_like(weight)
+            gw.index_add_(0, idx.view(-1), (-(g_loss * ctx.beta)) * diff)
+        return gz, gw, None
+
+
+class VectorQuantizer(nn.Module):
+    """Discretisation bottleneck of the VQ-VAE (reference: network/vqvae/quantizer.py:10)."""
+
+    onehot_limit_bytes = 2 << 30
+
+    def __init__(self, n_e, e_dim, beta, al):
+        super().__init__()
+        self.n_e = n_e
+        self.e_dim = e_dim
+        self.beta = beta
+        self.al = al
+        self.embedding = nn.Embedding(self.n_e, self.e_dim)
+        self.embedding.weight.data.uniform_(-1.0 / self.n_e, 1.0 / self.n_e)
+        self.path = _cabi.DVQ_PATH_AUTO      # DVQ_PATH_SIMT / DVQ_PATH_TC force a kernel
+        self.process_group = None            # set by dvq.dist.shard_module for the multi-GPU path
+        self._ws = None
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, z: torch.Tensor, weight: torch.Tensor):
+        if not isinstance(z, torch.Tensor):
+            raise TypeError("z must be a torch.Tensor")
+        if z.dtype != torch.float32:
+            raise TypeError("dvq.VectorQuantizer computes in fp32; got %s" % z.dtype)
+        if not z.is_cuda or not weight.is_cuda:
+            raise ValueError("dvq.VectorQuantizer has no CPU path: z and the codebook must be CUDA tensors "
+                             "(got z on %s, codebook on %s)" % (z.device, weight.device))
+        if z.device != weight.device:
+            raise ValueError("z (%s) and the codebook (%s) are on different devices" % (z.device, weight.device))
+        if not z.is_contiguous():
+            raise ValueError("z must be contiguous (the reference's .view(-1, e_dim) has the same requirement)")
+        if z.numel() % self.e_dim != 0:
+            raise RuntimeError("shape '[-1, %d]' is invalid for input of size %d" % (self.e_dim, z.numel()))
+        if weight.dtype != torch.float32 or not weight.is_contiguous() or tuple(weight.shape) != (self.n_e, self.e_dim):
+            raise ValueError("embedding.weight must be a contiguous fp32 [n_e, e_dim] tensor")
+
+    def _workspace(self, n: int, flags: int, device) -> torch.Tensor:
+        need = _cabi.vq_workspace_bytes(n, self.n_e, self.e_dim, flags)
+        ws = self._ws
+        if ws is None or ws.device != device or ws.numel() < need:
+            ws = torch.empty(max(need, 256), dtype=torch.uint8, device=device)
+            self._ws = ws
+        return ws
+
+    def _launch(self, z, weight, flags, z_q, idx, onehot, stats):
+        n = z.numel() // self.e_dim
+        ws = self._workspace(n, flags, z.device)
+        hist_ptr = stats.data_ptr() if stats is not None else None
+        sse_ptr = stats.data_ptr() + 8 * self.n_e if stats is not None else None
+        with torch.cuda.device(z.device):
+            _cabi.check(_cabi.lib.dvq_vq_forward(
+                z.data_ptr(), weight.data_ptr(), n, self.n_e, self.e_dim, flags,
+                z_q.data_ptr(), idx.data_ptr(), onehot.data_ptr() if onehot is not None else None,
+                hist_ptr, sse_ptr, ws.data_ptr(), ws.numel(), _stream_ptr(z.device)), "dvq_vq_forward")
+
+    def _forward_train_raw(self, z, weight):
+        n = z.numel() // self.e_dim
+        dev = z.device
+        z_q = torch.empty_like(z)
+        idx = torch.empty((n, 1), dtype=torch.int64, device=dev)
+        # stats = hist[K] (uint64) | sse (float64), one buffer so the all-reduce is one message
+        stats = torch.zeros(self.n_e + 1, dtype=torch.int64, device=dev)
+        self._launch(z, weight, _cabi.DVQ_TRAIN | self.path, z_q, idx, None, stats)
+        n_total = n
+        if self.process_group is not None:
+            n_total = _dist.allreduce_stats(stats, self.n_e, n, self.process_group)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib.dvq_vq_finalize(
+                stats.data_ptr(), stats.data_ptr() + 8 * self.n_e, n_total, self.n_e, self.e_dim,
+                float(self.al), float(self.beta), out.data_ptr(), out.data_ptr() + 4, _stream_ptr(dev)),
+                "dvq_vq_finalize")
+        self.last_stats = stats
+        return out[0], z_q, out[1], idx
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, z, istrain):
+        weight = self.embedding.weight
+        self._check(z, weight)
+        n = z.numel() // self.e_dim
+        if not istrain:
+            # quantizer.py:44-54
+            wd = weight.detach()
+            z_q = torch.empty_like(z)
+            idx = torch.empty((n, 1), dtype=torch.int64, device=z.device)
+            self._launch(z.detach(), wd, self.path, z_q, idx, None, None)
+            return idx, z_q
+
+        # quantizer.py:35-43, 56-67
+        if n == 0:  # torch.mean over an empty tensor is NaN in the reference as well
+            nan = torch.full((), float("nan"), device=z.device)
+            return nan, torch.empty_like(z), nan.clone(), torch.empty((0, self.n_e), device=z.device), \
+                torch.empty((0, 1), dtype=torch.int64, device=z.device)
+        if torch.is_grad_enabled() and (z.requires_grad or weight.requires_grad):
+            loss, z_q, ppl, idx = _VQFunction.apply(z, weight, self)
+        else:
+            loss, z_q, ppl, idx = self._forward_train_raw(z.detach(), weight.detach())
+        if n * self.n_e * 4 <= self.onehot_limit_bytes:
+            enc = torch.empty((n, self.n_e), dtype=torch.float32, device=z.device)
+            _onehot_into(idx, self.n_e, enc)
+        else:
+            enc = LazyOneHot(idx, self.n_e)
+        return loss, z_q, ppl, enc, idx
+
+    def get_emb(self, min_encoding_indices, dim):
+        """quantizer.py:68-75: index -> embedding.  Returns ``[B, dim]`` (``[1, dim]`` for the
+        reference's single-index call)."""
+        weight = self.embedding.weight.detach()
+        if not weight.is_cuda:
+            raise ValueError("dvq.VectorQuantizer has no CPU path: the codebook must be on a CUDA device")
+        idx = torch.as_tensor(min_encoding_indices, device=weight.device).reshape(-1).to(torch.int64).contiguous()
+        if dim != self.e_dim:
+            raise RuntimeError("shape '[1, %d]' is invalid for an embedding of width %d" % (dim, self.e_dim))
+        out = torch.empty((idx.numel(), self.e_dim), dtype=torch.float32, device=weight.device)
+        oob = torch.zeros(1, dtype=torch.int32, device=weight.device)
+        with torch.cuda.device(weight.device):
+            _cabi.check(_cabi.lib.dvq_gather(weight.data_ptr(), idx.data_ptr(), idx.numel(), self.n_e, self.e_dim,
+                                             out.data_ptr(), oob.data_ptr(), _stream_ptr(weight.device)), "dvq_gather")
+        # same failure mode as the reference's scatter_ on CUDA: a device-side assert
+        torch._assert_async(oob[0] == 0, "dvq.get_emb: index out of range")
+        return out.view(-1, dim)

@@ -1,0 +1,138 @@
+/* dvq.h — C ABI of the B200-native D-VQVAE hot path (libdvq_sm100.so).
+ *
+ * The reference (florasion/D-VQVAE) is pure Python and has no FFI of its own;
+ * its boundary for this path is the Python class surface.  Each entry point
+ * below names the reference code it replaces (paths relative to the reference
+ * root).  The Python mirror of that surface lives in d-vqvae_b200/dvq/ and
+ * binds these symbols with ctypes — see INTEGRATION.md.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers on the current CUDA device unless the
+ *    name ends in _host; tensors are row-major and contiguous; fp32 unless said.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - Device entry points only enqueue work on `stream`: no host synchronisation,
+ *    no allocation; the caller owns every buffer including the workspace.
+ *  - Return value: 0 (DVQ_OK) or a negative DvqStatus; a human-readable message
+ *    for the last failure on the calling thread is at dvq_last_error().
+ *  - There is no CPU fallback: on a machine without an sm_100 device the compute
+ *    entry points return DVQ_ERR_UNSUPPORTED_ARCH / DVQ_ERR_CUDA.
+ */
+#ifndef DVQ_H_
+#define DVQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVQ_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DVQ_API __attribute__((visibility("default")))
+#else
+#define DVQ_API
+#endif
+
+typedef enum DvqStatus {
+  DVQ_OK = 0,
+  DVQ_ERR_BAD_SHAPE = -1,
+  DVQ_ERR_BAD_ALIGN = -2,
+  DVQ_ERR_UNSUPPORTED_ARCH = -3,
+  DVQ_ERR_WORKSPACE = -4,
+  DVQ_ERR_CUDA = -5,
+  DVQ_ERR_NCCL = -6,
+  DVQ_ERR_BAD_ARG = -7
+} DvqStatus;
+
+/* flags for dvq_vq_forward / dvq_vq_workspace_bytes */
+#define DVQ_TRAIN 0x1         /* istrain=True: z_q = fl(z + fl(e - z)), accumulate hist + sse   */
+#define DVQ_WRITE_ONEHOT 0x2  /* also materialise min_encodings [N,K] fp32                      */
+#define DVQ_PATH_AUTO 0x00    /* tensor-core filter + exact refine when the shape allows        */
+#define DVQ_PATH_SIMT 0x10    /* force the all-FP32 CUDA-core kernel                            */
+#define DVQ_PATH_TC 0x20      /* force the tcgen05 kernel (error if the shape is unsupported)   */
+#define DVQ_PATH_MASK 0x30
+
+DVQ_API int dvq_abi_version(void);
+DVQ_API const char* dvq_last_error(void);
+
+/* Instrumentation for bench.py: number of kernels this library has launched in the process, and
+ * (when enabled) CUDA-event times of the stages of the calling thread's dvq_vq_forward calls,
+ * averaged over the calls since dvq_profile_enable(1) (at most 128 are kept):
+ * ms[0] code norms, ms[1] main kernel (tcgen05 filter or FP32 kernel), ms[2] FP32 refine,
+ * ms[3] one-hot; count[i] = calls averaged.  Events are recorded on the launching stream;
+ * dvq_profile_mean synchronises on them. */
+DVQ_API long long dvq_launch_count(void);
+DVQ_API int dvq_profile_enable(int on);
+DVQ_API int dvq_profile_mean(float* ms, int* count, int n);
+
+/* Device probe: SM count and compute capability of the current device. */
+DVQ_API int dvq_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- VectorQuantizer.forward — network/vqvae/quantizer.py:30-67 -------------------------
+ * d = fl(fl(sum z^2 + sum e^2) - 2 z.e) (:36-38), idx = first argmin (:39), z_q = E[idx]
+ * (:43/:53) or z + (z_q - z) (:60); the N x K distance matrix is never materialised.
+ *   z [N,D], E [K,D]  ->  z_q [N,D], idx [N] int64 (== the reference's [N,1]),
+ *   onehot [N,K] or NULL (:40-42), hist [K] += code usage, sse [1] += sum (e-z)^2.
+ * hist/sse must be zeroed by the caller before the first shard and are only touched
+ * under DVQ_TRAIN (they may be NULL otherwise).  Splitting forward from finalize lets a
+ * multi-GPU caller all-reduce (hist, sse) in between (dvq_allreduce_stats). */
+DVQ_API int dvq_vq_workspace_bytes(int64_t N, int K, int D, int flags, size_t* bytes);
+DVQ_API int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int flags,
+                   float* z_q, int64_t* idx, float* onehot,
+                   unsigned long long* hist, double* sse,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* loss = al*mean((z_q-z)^2) + beta*mean((z_q-z)^2) (quantizer.py:56-57),
+ * perplexity = exp(-sum p log(p+1e-10)), p = hist/N_total (:63-64). */
+DVQ_API int dvq_vq_finalize(const unsigned long long* hist, const double* sse, int64_t N_total, int K, int D,
+                    float al, float beta, float* loss, float* perplexity, void* stream);
+
+/* VectorQuantizer.get_emb — quantizer.py:68-75 (batched meaning: out[n,:] = E[idx[n],:]).
+ * Out-of-range indices set *oob (device int, may be NULL) and write zeros. */
+DVQ_API int dvq_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, float* out, int* oob, void* stream);
+
+/* min_encodings — quantizer.py:40-42: out[n,k] = (k == idx[n]) as fp32, every element written
+ * once (no memset + scatter).  Separate entry so the [N,K] matrix can be produced on demand. */
+DVQ_API int dvq_onehot(const int64_t* idx, int64_t N, int K, float* out, void* stream);
+
+/* Host-buffer (end-to-end) form of the same forward: z_host/E_host/zq_host/idx_host are
+ * HOST pointers (pinned for full overlap).  Rows are streamed through the GPU in chunks on
+ * three internal streams (H2D, compute, D2H).  loss/perplexity are host floats (train only). */
+typedef struct DvqHostCtx DvqHostCtx;
+DVQ_API int dvq_host_ctx_create(int64_t chunk_rows, int K_max, int D_max, DvqHostCtx** ctx);
+DVQ_API int dvq_host_ctx_destroy(DvqHostCtx* ctx);
+DVQ_API int dvq_vq_forward_host(DvqHostCtx* ctx, const float* z_host, const float* E_host, int64_t N, int K, int D,
+                        int flags, float al, float beta, float* zq_host, int64_t* idx_host,
+                        float* loss_host, float* perplexity_host);
+
+/* ---- PointNetEncoder.forward — network/pointnet_encoder.py:140-169 (+STN3d :27-45) ------
+ * Eval mode, global_feat=True, feature_transform=False.  BatchNorm is folded into the
+ * preceding conv/linear by the caller: W' = W*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta.
+ *   x [B,C,P] (C = 3 or 4)  ->  feat [B,1024], trans [B,3,3]. */
+typedef struct DvqPointNetWeights {
+  const float *stn_w1, *stn_b1;       /* [64,C],   [64]   conv1+bn1 (ReLU)   :29 */
+  const float *stn_w2, *stn_b2;       /* [128,64], [128]  conv2+bn2 (ReLU)   :30 */
+  const float *stn_w3, *stn_b3;       /* [1024,128],[1024] conv3+bn3 (ReLU)  :31 */
+  const float *stn_fc1_w, *stn_fc1_b; /* [512,1024],[512] fc1+bn4 (ReLU)     :35 */
+  const float *stn_fc2_w, *stn_fc2_b; /* [256,512],[256]  fc2+bn5 (ReLU)     :36 */
+  const float *stn_fc3_w, *stn_fc3_b; /* [9,256], [9]     fc3; +I by kernel  :37-43 */
+  const float *w1, *b1;               /* [64,C]    conv1+bn1 (ReLU)          :150 */
+  const float *w2, *b2;               /* [128,64]  conv2+bn2 (ReLU)          :161 */
+  const float *w3, *b3;               /* [1024,128] conv3+bn3 (no ReLU)      :162 */
+} DvqPointNetWeights;
+DVQ_API int dvq_pointnet_workspace_bytes(int B, int C, int P, size_t* bytes);
+DVQ_API int dvq_pointnet_forward(const float* x, const DvqPointNetWeights* w, int B, int C, int P,
+                         float* feat, float* trans, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the one collective of the sharded path ---------------------------------
+ * In-place sum over ranks of hist [K] (uint64) and sse [1] (double) on `nccl_comm`
+ * (an ncclComm_t passed as void*), enqueued on `stream`.  libnccl is resolved at run time
+ * (dlopen of the already-loaded library); DVQ_ERR_NCCL if it cannot be found. */
+DVQ_API int dvq_allreduce_stats(void* nccl_comm, unsigned long long* hist, double* sse, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVQ_H_ */

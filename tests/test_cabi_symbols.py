@@ -1,0 +1,106 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dvq.h declares; argument
+validation that needs no device works; the product path fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "dvq.h")).read()
+    return sorted(set(re.findall(r"DVQ_API\s+[\w\s\*]+?\b(dvq_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dvq import _cabi
+    names = _declared()
+    assert len(names) >= 14
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(_cabi.SYMBOLS), (set(names) ^ set(_cabi.SYMBOLS))
+    assert lib.dvq_abi_version() == _cabi.ABI_VERSION
+
+
+def test_workspace_queries_and_shape_errors_need_no_device():
+    from dvq import _cabi
+    assert _cabi.vq_workspace_bytes(4096, 512, 64, 0) >= 512 * 4
+    assert _cabi.vq_workspace_bytes(0, 1, 1, _cabi.DVQ_PATH_SIMT) > 0
+    assert _cabi.pointnet_workspace_bytes(8, 4, 3000) >= 8 * 1024 * 4 * 2
+    with pytest.raises(RuntimeError, match="BAD_SHAPE"):
+        _cabi.vq_workspace_bytes(10, 0, 64, 0)
+    with pytest.raises(RuntimeError, match="BAD_SHAPE"):
+        _cabi.pointnet_workspace_bytes(1, 5, 100)
+    sz = ctypes.c_size_t()
+    assert _cabi.lib.dvq_vq_workspace_bytes(1 << 40, 8, 8, 0, ctypes.byref(sz)) == -1
+    assert "2^31" in _cabi.last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_silent_cpu_fallback():
+    import dvq
+    from dvq import _cabi
+    vq = dvq.VectorQuantizer(16, 8, 0.25, 1)
+    with pytest.raises(ValueError, match="no CPU path"):
+        vq(torch.randn(4, 8), True)
+    with pytest.raises(ValueError, match="no CPU path"):
+        vq(torch.randn(4, 8), False)
+    with pytest.raises(ValueError, match="no CPU path"):
+        vq.get_emb(torch.tensor([1]), 8)
+    pn = dvq.PointNetEncoder(channel=4).eval()
+    with pytest.raises(ValueError, match="no CPU path"):
+        pn(torch.randn(1, 4, 16))
+    # straight through the C ABI: the library refuses, it does not compute on the host
+    buf = (ctypes.c_float * 64)()
+    idx = (ctypes.c_int64 * 4)()
+    ws = ctypes.create_string_buffer(4096 + 256)
+    wsp = (ctypes.addressof(ws) + 255) // 256 * 256
+    rc = _cabi.lib.dvq_vq_forward(ctypes.addressof(buf), ctypes.addressof(buf), 4, 2, 8, 0, ctypes.addressof(buf),
+                                  ctypes.addressof(idx), None, None, None, wsp, 4096, None)
+    assert rc in (-3, -5), rc
+
+
+def test_module_surface_matches_reference():
+    """Constructor args, attribute names, state_dict keys."""
+    import dvq
+    vq = dvq.VectorQuantizer(128, 256, 0.25, 1)
+    assert (vq.n_e, vq.e_dim, vq.beta, vq.al) == (128, 256, 0.25, 1)
+    assert list(vq.state_dict()) == ["embedding.weight"] and vq.embedding.weight.shape == (128, 256)
+    assert float(vq.embedding.weight.abs().max()) <= 1.0 / 128
+    w = dvq.VQVAE(128, 32, 2, 128, 1024, 2, a=0)
+    assert list(w.state_dict()) == ["vector_quantization.embedding.weight"]
+    assert w.vector_quantization.al == 0 and w.vector_quantization.beta == 2
+    pn = dvq.PointNetEncoder(global_feat=True, feature_transform=False, channel=4)
+    keys = list(pn.state_dict())
+    expected = []
+    for pre, fcs in (("stn.", True), ("", False)):
+        for c in ("conv1", "conv2", "conv3") + (("fc1", "fc2", "fc3") if fcs else ()):
+            expected += [pre + c + ".weight", pre + c + ".bias"]
+        for b in ("bn1", "bn2", "bn3") + (("bn4", "bn5") if fcs else ()):
+            expected += [pre + b + s for s in (".weight", ".bias", ".running_mean", ".running_var", ".num_batches_tracked")]
+    assert sorted(keys) == sorted(expected)
+    assert pn.stn.conv1.weight.shape == (64, 4, 1) and pn.conv3.weight.shape == (1024, 128, 1)
+    from oracle import pointnet_oracle as po
+    sd = {k: torch.from_numpy(v) for k, v in po.make_state(1, 4).items()}
+    pn.load_state_dict(sd, strict=True)          # reference-keyed checkpoint loads unchanged
+    with pytest.raises(NotImplementedError):
+        dvq.PointNetEncoder(global_feat=False)
+
+
+def test_bn_fold_matches_oracle_math():
+    import numpy as np
+    import dvq
+    from dvq.pointnet import _fold
+    from oracle import pointnet_oracle as po
+    sd = po.make_state(3, 4)
+    pn = dvq.PointNetEncoder(channel=4).eval()
+    pn.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    w, b = _fold(pn.conv2.weight, pn.conv2.bias, pn.bn2)
+    x = np.random.RandomState(0).standard_normal((1, 64, 7)).astype(np.float32)
+    ref = po._bn_eval(po._conv1x1(x, sd["conv2.weight"], sd["conv2.bias"]), sd, "bn2")
+    got = np.einsum("oc,bcp->bop", w.numpy(), x) + b.numpy()[None, :, None]
+    assert np.abs(got - ref).max() < 1e-5

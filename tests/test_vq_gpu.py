@@ -1,0 +1,232 @@
+"""GPU parity tests of the VQ path (run on the B200 box: pytest -m gpu).  Every call goes through
+the C ABI (dvq.* modules are ctypes front-ends).  Checker = oracle/ + golden vectors of the real
+reference.  Bars: indices identical outside the FP64 near-tie band (rel gap < 1e-6), z_q bit-exact
+given the index, loss / perplexity within 1e-5 relative."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vq_oracle as vo
+from _cases import VQ_CASES, load_gold, rel_err, vq_inputs
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def _paths():
+    from dvq import _cabi
+    return [("simt", _cabi.DVQ_PATH_SIMT), ("auto", _cabi.DVQ_PATH_AUTO)]
+
+
+def _module(E, al, beta, path):
+    import dvq
+    m = dvq.VectorQuantizer(E.shape[0], E.shape[1], beta, al).cuda()
+    with torch.no_grad():
+        m.embedding.weight.copy_(torch.from_numpy(E))
+    m.path = path
+    return m
+
+
+@pytest.mark.parametrize("pname,path", _paths() if torch.cuda.is_available() else [("simt", 0x10)])
+@pytest.mark.parametrize("name", list(VQ_CASES))
+def test_forward_matches_reference_golden(name, pname, path):
+    z, E, al, beta = vq_inputs(name)
+    g = load_gold(name)
+    m = _module(E, al, beta, path)
+    zt = torch.from_numpy(z).cuda()
+    with torch.no_grad():
+        loss, zq, ppl, enc, idx = m(zt, True)
+        idx_i, zq_i = m(zt, False)
+    assert idx.shape == g["idx_train"].shape and idx.dtype == torch.int64
+    assert zq.shape == zt.shape and zq_i.shape == zt.shape and loss.dim() == 0 and ppl.dim() == 0
+    idx_n, idxi_n = idx.cpu().numpy(), idx_i.cpu().numpy()
+    n_mis, n_bad, worst = vo.allowed_index_mismatch(z, E, idx_n, g["idx_train"])
+    assert n_bad == 0, (n_mis, worst)
+    assert vo.allowed_index_mismatch(z, E, idxi_n, g["idx_infer"])[1] == 0
+    assert np.array_equal(idx_n, idxi_n)
+    # z_q bit-exact given OUR index (oracle arithmetic), and bit-equal to the reference where indices agree
+    assert np.array_equal(zq_i.cpu().numpy().view(np.uint32), vo.zq_infer_from_idx(E, idx_n).reshape(z.shape).view(np.uint32))
+    assert np.array_equal(zq.cpu().numpy().view(np.uint32), vo.zq_train_from_idx(z, E, idx_n).reshape(z.shape).view(np.uint32))
+    same = idx_n.reshape(-1) == g["idx_train"].reshape(-1)
+    assert np.array_equal(zq.cpu().numpy().reshape(-1, E.shape[1])[same].view(np.uint32),
+                          g["zq_train"].reshape(-1, E.shape[1])[same].view(np.uint32))
+    assert rel_err(loss.item(), g["loss"]) < REL
+    if n_mis == 0:
+        assert rel_err(ppl.item(), g["perplexity"]) < REL
+    hist = np.bincount(idx_n.reshape(-1), minlength=E.shape[0])
+    assert rel_err(ppl.item(), vo.perplexity_from_hist(hist, idx_n.shape[0])) < REL
+    # min_encodings: fp32 one-hot [N,K] (quantizer.py:40-42)
+    assert enc.dtype == torch.float32 and tuple(enc.shape) == (idx_n.shape[0], E.shape[0])
+    assert np.array_equal(enc.cpu().numpy(), vo.one_hot(idx_n, E.shape[0]))
+    stats = m.last_stats.cpu().numpy()
+    assert np.array_equal(stats[:E.shape[0]], hist)
+
+
+def test_exact_ties_pick_lowest_index():
+    z, E, al, beta = vq_inputs("vq_dupes")
+    for _, path in _paths():
+        m = _module(E, al, beta, path)
+        idx, _ = m(torch.from_numpy(z).cuda(), False)
+        assert int(idx.max()) < E.shape[0] // 2
+
+
+@pytest.mark.parametrize("pname,path", _paths() if torch.cuda.is_available() else [("simt", 0x10)])
+def test_config1_full_size(pname, path):
+    """BASELINE config 1 (N=65536, D=64, K=512), BASELINE.md recipe, all rows against the real
+    reference's indices; known answers loss 1.248528003692627 / perplexity 455.29669189453125."""
+    g = load_gold("vq_config1_full")
+    torch.manual_seed(0)
+    emb = torch.nn.Embedding(512, 64)
+    emb.weight.data.uniform_(-1.0 / 512, 1.0 / 512)
+    z = torch.randn(65536, 64)
+    if hashlib.sha256(z.numpy().tobytes()).hexdigest() != str(g["z_sha256"]):
+        pytest.skip("torch CPU RNG stream differs from the build container")
+    E = emb.weight.detach().numpy()
+    m = _module(E, 1, 0.25, path)
+    m.onehot_limit_bytes = 0
+    with torch.no_grad():
+        loss, zq, ppl, enc, idx = m(z.cuda(), True)
+    n_mis, n_bad, worst = vo.allowed_index_mismatch(z.numpy(), E, idx.cpu().numpy(), g["idx"].astype(np.int64))
+    assert n_bad == 0 and n_mis < 200, (n_mis, worst)
+    assert rel_err(loss.item(), 1.248528003692627) < REL
+    assert rel_err(ppl.item(), 455.29669189453125) < REL
+    assert type(enc).__name__ == "LazyOneHot" and tuple(enc.shape) == (65536, 512)
+    assert torch.equal(enc.materialize().argmax(1, keepdim=True), idx)
+    same = (idx.cpu().numpy().reshape(-1) == g["idx"].astype(np.int64))
+    ref_zq = vo.zq_train_from_idx(z.numpy(), E, g["idx"].astype(np.int64))
+    assert np.array_equal(zq.cpu().numpy()[same].view(np.uint32), ref_zq[same].view(np.uint32))
+
+
+@pytest.mark.parametrize("pname,path", _paths() if torch.cuda.is_available() else [("simt", 0x10)])
+@pytest.mark.parametrize("variant", ["default", "variant_b"])
+def test_config2_full_size_properties(variant, pname, path):
+    """BASELINE config 2 (N=4M, D=64, K=512): size-independent properties on all rows + an
+    oracle check (band rule) on a 65 536-row seeded subsample."""
+    N, K, D = 4194304, 512, 64
+    gen = torch.Generator(device="cuda").manual_seed(2000)
+    if variant == "default":
+        E = (torch.rand(K, D, device="cuda", generator=gen) * 2 - 1) / K
+        z = torch.randn(N, D, device="cuda", generator=gen)
+    else:
+        E = torch.randn(K, D, device="cuda", generator=gen)
+        z = E[torch.randint(0, K, (N,), device="cuda", generator=gen)] + 0.1 * torch.randn(N, D, device="cuda", generator=gen)
+    m = _module(E.cpu().numpy(), 1.0, 0.25, path)
+    with torch.no_grad():
+        loss, zq, ppl, enc, idx = m(z, True)
+        idx_i, zq_i = m(z, False)
+    assert type(enc).__name__ == "LazyOneHot"
+    flat = idx.view(-1)
+    assert int(flat.min()) >= 0 and int(flat.max()) < K and torch.equal(idx, idx_i)
+    e = E[flat]
+    assert torch.equal(zq_i, e)                                        # gather bit-exact
+    assert torch.equal(zq, z + (e - z))                                # two roundings, no FMA
+    hist = torch.bincount(flat, minlength=K)
+    assert int(hist.sum()) == N
+    assert torch.equal(m.last_stats[:K], hist)                         # checksum of checksums
+    mse = ((e - z).double() ** 2).mean().item()
+    assert rel_err(loss.item(), np.float32(np.float32(1.0) * np.float32(mse) + np.float32(0.25) * np.float32(mse))) < REL
+    p = hist.double() / N
+    assert rel_err(ppl.item(), torch.exp(-(p * torch.log(p + 1e-10)).sum()).item()) < REL
+    # idempotence: quantising z_q returns the same codes with zero error
+    idx2, zq2 = m(zq_i, False)
+    d_self = vo.allowed_index_mismatch(zq_i[:65536].cpu().numpy(), E.cpu().numpy(), idx2[:65536].cpu().numpy(), idx[:65536].cpu().numpy())
+    assert d_self[1] == 0
+    # oracle on a seeded subsample spread over the whole tensor
+    rows = torch.from_numpy(np.random.RandomState(7).choice(N, 65536, replace=False)).cuda()
+    zs = z[rows].cpu().numpy()
+    ridx, _ = vo.forward_infer(zs, E.cpu().numpy())
+    n_mis, n_bad, worst = vo.allowed_index_mismatch(zs, E.cpu().numpy(), flat[rows].cpu().numpy(), ridx)
+    assert n_bad == 0, (n_mis, worst)
+
+
+def test_get_emb_and_wrapper_api():
+    import dvq
+    z, E, al, beta = vq_inputs("vq_k128_d256")
+    g = load_gold("vq_get_emb")
+    w = dvq.VQVAE(128, 32, 2, 128, 256, 0.25, a=1).cuda()
+    with torch.no_grad():
+        w.vector_quantization.embedding.weight.copy_(torch.from_numpy(E))
+    for p, ref in zip(g["picks"], g["embs"]):
+        out = w.get_embbeding(torch.tensor([int(p)], device="cuda"), 256)      # gen_net.py:101-106 call shape
+        assert tuple(out.shape) == (1, 256)
+        assert np.array_equal(out.cpu().numpy()[0].view(np.uint32), ref.view(np.uint32))
+    batch = w.get_embbeding(torch.from_numpy(g["picks"]).cuda(), 256)          # batched meaning
+    assert np.array_equal(batch.cpu().numpy().view(np.uint32), g["embs"].view(np.uint32))
+    with torch.no_grad():
+        l3 = w(torch.from_numpy(z).cuda())
+        i2 = w.inference(torch.from_numpy(z).cuda())
+    assert len(l3) == 3 and len(i2) == 2
+    assert rel_err(l3[0].item(), g["wrapper_loss"]) < REL and rel_err(l3[2].item(), g["wrapper_ppl"]) < REL
+    assert vo.allowed_index_mismatch(z, E, i2[0].cpu().numpy(), g["wrapper_idx"])[1] == 0
+
+
+def test_backward_matches_reference_formulas():
+    """Autograd through the fused forward == autograd through the reference's torch ops."""
+    z, E, al, beta = vq_inputs("vq_ragged")
+    m = _module(E, al, beta, 0x10)
+    zt = torch.from_numpy(z).cuda().requires_grad_(True)
+    loss, zq, ppl, enc, idx = m(zt, True)
+    (loss * 3.0 + (zq * zq).sum()).backward()
+    zr = torch.from_numpy(z).cuda().requires_grad_(True)
+    W = torch.from_numpy(E).cuda().requires_grad_(True)
+    e = W[idx.view(-1)]
+    l_ref = al * torch.mean((e.detach() - zr) ** 2) + beta * torch.mean((e - zr.detach()) ** 2)
+    zq_ref = zr + (e - zr).detach()
+    (l_ref * 3.0 + (zq_ref * zq_ref).sum()).backward()
+    assert torch.allclose(zt.grad, zr.grad, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(m.embedding.weight.grad, W.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_input_validation_and_abi_errors():
+    import dvq
+    from dvq import _cabi
+    m = dvq.VectorQuantizer(16, 8, 0.25, 1).cuda()
+    with pytest.raises(TypeError):
+        m(torch.randn(4, 8, device="cuda").half(), True)
+    with pytest.raises(RuntimeError, match="invalid for input of size"):
+        m(torch.randn(3, 7, device="cuda"), True)
+    with pytest.raises(ValueError, match="contiguous"):
+        m(torch.randn(8, 4, device="cuda").t(), True)
+    l, q, p, e, i = m(torch.empty(0, 8, device="cuda"), True)
+    assert tuple(q.shape) == (0, 8) and tuple(i.shape) == (0, 1)
+    i0, q0 = m(torch.empty(0, 8, device="cuda"), False)
+    assert tuple(i0.shape) == (0, 1)
+    z = torch.randn(32, 8, device="cuda")
+    zq = torch.empty_like(z)
+    idx = torch.empty(32, dtype=torch.int64, device="cuda")
+    ws = torch.empty(256, dtype=torch.uint8, device="cuda")
+    rc = _cabi.lib.dvq_vq_forward(z.data_ptr(), m.embedding.weight.data_ptr(), 32, 16, 8, 0, zq.data_ptr(), idx.data_ptr(),
+                                  None, None, None, ws.data_ptr(), 16, None)
+    assert rc == -4 and "workspace too small" in _cabi.last_error()
+    rc = _cabi.lib.dvq_vq_forward(z.data_ptr(), m.embedding.weight.data_ptr(), 32, 16, 8, _cabi.DVQ_TRAIN, zq.data_ptr(),
+                                  idx.data_ptr(), None, None, None, ws.data_ptr(), 256, None)
+    assert rc == -7
+    sm, major, minor = _cabi.device_info()
+    assert major == 10 and sm > 100
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_host_buffer_entry_equals_device_entry(train):
+    """dvq_vq_forward_host (chunked, 3-stream pipeline, ragged last chunk) == dvq_vq_forward."""
+    import dvq
+    N, K, D = 100000 + 37, 512, 64
+    rs = np.random.RandomState(5)
+    E = vo.default_codebook(K, D, 5)
+    z = rs.standard_normal((N, D)).astype(np.float32)
+    hq = dvq.HostQuantizer(chunk_rows=16384, n_e_max=K, e_dim_max=D)
+    zt = torch.from_numpy(z).pin_memory()
+    Et = torch.from_numpy(E).pin_memory()
+    m = _module(E, 1.0, 0.25, 0)
+    with torch.no_grad():
+        if train:
+            loss_h, zq_h, ppl_h, idx_h = hq.forward(zt, Et, True, 1.0, 0.25)
+            loss, zq, ppl, _, idx = m(zt.cuda(), True)
+            assert rel_err(loss_h, loss.item()) < 1e-6 and rel_err(ppl_h, ppl.item()) < 1e-6
+        else:
+            idx_h, zq_h = hq.forward(zt, Et, False)
+            idx, zq = m(zt.cuda(), False)
+    assert torch.equal(idx_h, idx.cpu()) and torch.equal(zq_h, zq.cpu())
+    hq.close()
