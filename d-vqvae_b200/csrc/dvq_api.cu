@@ -230,6 +230,17 @@ int dvq_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, floa
   return launch_gather(E, idx, N, K, D, out, oob, static_cast<cudaStream_t>(stream));
 }
 
+int dvq_debug_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, int ksteps,
+                   const uint32_t* strides, uint32_t idesc, int n_cols, float* out, int* err, void* stream) {
+  if (!a_img || !b_img || !strides || !out || !err) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
+  if (a_bytes % 16 || b_bytes % 16 || n_cols % 32 || n_cols <= 0 || n_cols > 256 || ksteps <= 0)
+    return fail(DVQ_ERR_BAD_SHAPE, "images must be multiples of 16 bytes, n_cols a multiple of 32 in (0,256]");
+  if ((size_t)a_bytes + b_bytes > 200 * 1024) return fail(DVQ_ERR_BAD_SHAPE, "operand images exceed 200 KB");
+  int rc = require_sm100();
+  if (rc) return rc;
+  return launch_umma_probe(a_img, a_bytes, b_img, b_bytes, ksteps, strides, idesc, n_cols, out, err, static_cast<cudaStream_t>(stream));
+}
+
 int dvq_onehot(const int64_t* idx, int64_t N, int K, float* out, void* stream) {
   if (N < 0 || K <= 0) return fail(DVQ_ERR_BAD_SHAPE, "need N >= 0, K > 0");
   if (N > 0 && (!idx || !out)) return fail(DVQ_ERR_BAD_ARG, "NULL argument");

@@ -69,6 +69,9 @@ int launch_finalize(const unsigned long long* hist, const double* sse, int64_t N
 int launch_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, float* out, int* oob,
                   cudaStream_t s);
 
+int launch_umma_probe(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, int ksteps,
+                      const uint32_t* strides, uint32_t idesc, int n_cols, float* out, int* err, cudaStream_t s);
+
 // PointNet
 size_t pointnet_workspace_bytes(int B, int C, int P);
 int launch_pointnet(const float* x, const DvqPointNetWeights* w, int B, int C, int P, float* feat,

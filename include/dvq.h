@@ -67,6 +67,13 @@ DVQ_API long long dvq_launch_count(void);
 DVQ_API int dvq_profile_enable(int on);
 DVQ_API int dvq_profile_mean(float* ms, int* count, int n);
 
+/* Diagnostic used by tests/test_tc_probe_gpu.py: run `ksteps` tcgen05.mma (M=128, N=n_cols,
+ * kind::f16) on caller-built shared-memory operand images and dump the [128,n_cols] fp32
+ * accumulator.  strides = {a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep} in bytes; *err (device
+ * int) is set non-zero if the MMA never signalled completion (bounded wait, no hang). */
+DVQ_API int dvq_debug_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, int ksteps,
+                           const uint32_t* strides, uint32_t idesc, int n_cols, float* out, int* err, void* stream);
+
 /* Device probe: SM count and compute capability of the current device. */
 DVQ_API int dvq_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
