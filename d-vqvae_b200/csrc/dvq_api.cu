@@ -213,6 +213,18 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
   return DVQ_OK;
 }
 
+int dvq_vq_read_counters(const void* workspace, int64_t N, int K, int D, int flags, int* out4) {
+  if (!workspace || !out4) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
+  int rc = check_vq_shape(N, K, D);
+  if (rc) return rc;
+  out4[0] = out4[1] = out4[2] = out4[3] = 0;
+  const bool use_tc = vq_tc_supported(N, K, D) && (flags & DVQ_PATH_MASK) != DVQ_PATH_SIMT;
+  if (!use_tc) return DVQ_OK;
+  const VqWorkspace w = vq_workspace_layout(N, K, D, flags);
+  DVQ_CUDA_CHECK(cudaMemcpy(out4, static_cast<const char*>(workspace) + w.off_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  return DVQ_OK;
+}
+
 int dvq_vq_finalize(const unsigned long long* hist, const double* sse, int64_t N_total, int K, int D, float al,
                     float beta, float* loss, float* perplexity, void* stream) {
   if (!hist || !sse || !loss || !perplexity) return fail(DVQ_ERR_BAD_ARG, "NULL argument");

@@ -1,11 +1,575 @@
-// tcgen05 filter kernel — placeholder until the tensor-core path lands.
+// tcgen05 VQ kernel: tensor-core distance filter fused with the row argmin, the codebook gather,
+// the straight-through / SSE reduction and the usage histogram.  The rows whose winner the filter
+// cannot decide *rigorously* are appended to a device-side list and re-evaluated by the exact
+// FP32 kernel (vq_simt_fp32.cu) — "filter and refine" (SURVEY §7.4).
+//
+// Contraction.  For a 128-row tile the accumulator is
+//     acc[n,k] = g_n * (B_n + ee_k) - 2 z'_n . e'_k        (z' = s_n z, e' = s_E e, g_n = s_n s_E)
+// with power-of-two scales s_n (per row) and s_E (per codebook) that put every operand inside the
+// FP16 range, ee_k = ||e_k||^2 and the bias B_n >= 2 |z_n| max_k|e_k| which keeps acc >= 0.
+// It is ONE chain of tcgen05.mma (kind::f16, FP32 accumulate in TMEM, M=128, N<=256, K=16):
+//     A row  = [ zh (D) | zl (D) | fold (16) ]     zh = fp16(z'), zl = fp16(z' - zh)  (22-bit z)
+//     B row  = [ eh (D) |          fold (16) ]     eh = fp16(-2 e')
+// issued as zh.eh + zl.eh + fold.fold; the fold columns carry g_n*B_n and g_n*ee_k as products of
+// FP16 pairs (ee_k split in three FP16 terms).  Because acc >= 0 its bit pattern is monotone, so the
+// epilogue packs the 5-bit local column index into the low mantissa bits and takes FMNMX3 minima.
+//
+// Rigor.  eps_n bounds |acc - exact| for every k of row n (operand rounding: |z'| * max_k||eh_k+2e'_k||
+// measured exactly by the prep kernel; FP16 lo-term rounding; tensor-core FP32 accumulation;
+// index packing; ee rounding).  A row is decided iff no other key lies within 2*eps_n of the
+// minimum; the count of such keys is kept with a running (never too small) threshold, exact
+// resets, and FFMA.SAT arithmetic on the FMA pipe.  Undecided rows (a few %) go to the list.
+//
+// Pipeline (one persistent CTA per SM, 14 warps):
+//   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B)
+//   warp 1      MMA      : single elected thread issues tcgen05.mma, commits to mbarriers
+//   warps 2-5   convert  : staging -> registers -> scales / norms / bounds -> FP16 A image (2 stages)
+//   warps 6-13  epilogue : tcgen05.ld TMEM -> keys -> argmin + ambiguity count; then gather
+//                          E[idx] (128-bit), z_q, SSE, smem histogram, idx (int64)
+// TMEM: 512 columns = 2 accumulator stages of 256, so the MMA of one 256-code chunk overlaps the
+// epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays resident in
+// shared memory for the life of the CTA.
+#include <cuda_fp16.h>
+
 #include "dvq_common.cuh"
+#include "tc_prims.cuh"
 
 namespace dvq {
-bool vq_tc_supported(int64_t, int, int) { return false; }
-size_t vq_tc_operand_bytes(int, int) { return 0; }
-int launch_vq_tc(const float*, const float*, const float*, int64_t, int, int, int, float*, int64_t*,
-                 unsigned long long*, double*, void*, int*, int*, cudaStream_t) {
-  return fail(DVQ_ERR_BAD_SHAPE, "tcgen05 path not built");
+namespace {
+
+constexpr int TM = 128;                 // rows per tile
+constexpr int A_CHUNK_BYTES = TM * 16 + 32;  // one 8-wide k-chunk of the A image (+32 B: bank spreading)
+constexpr int NUM_WARPS = 14;
+constexpr int NTHREADS = NUM_WARPS * 32;
+constexpr int EPI_WARP0 = 6;
+constexpr int CONV_WARP0 = 2;
+constexpr int META_SLOTS = 4;
+
+enum ErrCode { ERR_STAGE_FULL = 1, ERR_STAGE_EMPTY, ERR_A_FULL, ERR_A_EMPTY, ERR_ACC_FULL, ERR_ACC_EMPTY, ERR_B_FULL };
+
+struct CbMeta {          // written by the prep kernels, read by the main kernel
+  float s_E;             // power-of-two codebook scale
+  float b0;              // fp16-representable upper bound of s_E * max_k ||e_k||
+  float eh_norm_bound;   // >= max_k ||eh_k||
+  float delta_max;       // >= max_k ||eh_k - (-2 s_E e_k)||   (exact FP16 rounding residual)
+  int half_E;            // s_E = 2^(10 - half_E)
+  int degenerate;        // 1: codebook all-zero / non-finite -> every row goes to the exact kernel
+};
+
+struct TcParams {
+  const float* z;
+  const float* E;
+  const uint8_t* bimg;
+  const CbMeta* cb;
+  int64_t N;
+  int K, D, train;
+  float* zq;
+  int64_t* idx;
+  unsigned long long* hist;
+  double* sse;
+  int* counters;   // [0] refine-list length, [1] protocol error code
+  int* row_list;
+  uint32_t index_mask;  // 0xffffffe0 (kept in a register so key packing is one LOP3)
+  int64_t ntiles;
+};
+
+struct SmemLayout {
+  uint32_t bimg, a_img[2], stage[2], meta, fin, sidx, hist, total;
+  uint32_t bimg_bytes, a_bytes, stage_bytes;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int K, int D) {
+  SmemLayout L;
+  const uint32_t kc_b = (uint32_t)(D + 16) / 8, kc_a = (uint32_t)(2 * D + 16) / 8;
+  L.bimg_bytes = kc_b * (uint32_t)K * 16;
+  L.a_bytes = kc_a * A_CHUNK_BYTES;
+  L.stage_bytes = (uint32_t)TM * D * 4;
+  uint32_t off = 0;
+  L.bimg = off; off += (L.bimg_bytes + 127u) & ~127u;
+  L.a_img[0] = off; off += (L.a_bytes + 127u) & ~127u;
+  L.a_img[1] = off; off += (L.a_bytes + 127u) & ~127u;
+  L.stage[0] = off; off += L.stage_bytes;
+  L.stage[1] = off; off += L.stage_bytes;
+  L.meta = off; off += META_SLOTS * TM * 4;
+  L.fin = off; off += 2 * TM * 12;      // per half: key, col, cnt
+  L.sidx = off; off += TM * 4;
+  L.hist = off; off += (uint32_t)K * 4;
+  L.total = off;
+  return L;
 }
+
+// ------------------------------------------------------------------------------------------------
+// codebook preparation (tiny): scale, FP16 operand image, exact rounding residual
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, CbMeta* __restrict__ cb, int* __restrict__ counters) {
+  __shared__ float red[32];
+  float m = 0.f;
+  bool bad = false;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = ee[k];
+    if (!(v >= 0.f) || v > 1e30f) bad = true;
+    m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  bad = __syncthreads_or(bad);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    CbMeta c;
+    c.degenerate = (bad || !(m > 1e-30f)) ? 1 : 0;
+    const float emax = sqrtf(m) * (1.f + 1e-6f) ;
+    int ex = 0;
+    if (!c.degenerate) ex = (int)((__float_as_uint(emax) >> 23) & 255u) - 127;   // emax in [2^ex, 2^(ex+1))
+    c.half_E = ex;
+    c.s_E = c.degenerate ? 1.f : exp2f((float)(10 - ex));                        // s_E*emax in [2^10, 2^11)
+    c.b0 = __half2float(__float2half_ru(c.s_E * emax * (1.f + 1e-6f)));
+    c.eh_norm_bound = 2.f * c.s_E * emax * (1.f + 1.f / 512.f);
+    c.delta_max = 0.f;
+    *cb = c;
+    counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0;
+  }
+}
+
+// one warp per code: eh = fp16(-2 s_E e), fold columns, residual norm -> atomic max
+__global__ void tc_cb_image_kernel(const float* __restrict__ E, const float* __restrict__ ee, int K, int D,
+                                   CbMeta* __restrict__ cb, uint8_t* __restrict__ bimg) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= K) return;
+  const float sE = cb->s_E;
+  const float* row = E + (int64_t)warp * D;
+  float res = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = -2.f * sE * __ldg(row + d);
+    const __half h = __float2half_rn(v);
+    const float r = v - __half2float(h);       // exact
+    res = fmaf(r, r, res);
+    *reinterpret_cast<__half*>(bimg + (size_t)(d >> 3) * K * 16 + (size_t)warp * 16 + (d & 7) * 2) = h;
+  }
+  res = warp_sum(res);
+  if (lane < 16) {   // fold k-chunks D/8 and D/8+1
+    float v = 0.f;
+    const float q = (sE * __ldg(ee + warp)) * sE * (1.f / 256.f);   // this order cannot overflow
+    const float hi = __half2float(__float2half_rn(q));
+    const float mid = __half2float(__float2half_rn(q - hi));
+    const float lo = __half2float(__float2half_rn(q - hi - mid));
+    if (lane == 0) v = cb->b0;
+    if (lane == 1) v = hi;
+    if (lane == 2) v = mid;
+    if (lane == 3) v = lo;
+    const int d = D + lane;
+    *reinterpret_cast<__half*>(bimg + (size_t)(d >> 3) * K * 16 + (size_t)warp * 16 + (d & 7) * 2) = __float2half_rn(v);
+  }
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(&cb->delta_max), __float_as_int(sqrtf(res) * (1.f + 1e-5f)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_key(uint32_t v, uint32_t mask, uint32_t j) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(v), "r"(mask), "r"(j));   // (v & mask) | j
+  return r;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// barrier + AND-reduction of a predicate over the participating threads (error consensus)
+__device__ __forceinline__ bool named_bar_and(int id, int nthreads, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "bar.red.and.pred p, %1, %2, q;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+      : "memory");
+  return r != 0;
+}
+// whole-warp wait: lane 0 spins (bounded), then every lane performs its own (now immediate) acquire
+__device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volatile int* errw, int code) {
+  int ok = 1;
+  if ((threadIdx.x & 31) == 0) ok = tc::mbar_wait(bar, parity, errw, code) ? 1 : 0;
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (ok) {
+    for (int i = 0; i < 1024 && !tc::mbar_try_wait(bar, parity); ++i) {}
+  }
+  __syncwarp();
+  return ok != 0;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_stage_full[2], bar_stage_empty[2], bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2], bar_b_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int serr;
+
+  const SmemLayout L = smem_layout(p.K, p.D);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = p.D, K = p.K;
+  const int nk = D / 16;                       // k-steps per product
+  const int nchunks = (K + 255) / 256;         // accumulator chunks per tile
+  const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (tid == 0) {
+    serr = 0;
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bar_stage_full[i], 1);
+      tc::mbar_init(&bar_stage_empty[i], 128);
+      tc::mbar_init(&bar_a_full[i], 128);
+      tc::mbar_init(&bar_a_empty[i], 1);
+      tc::mbar_init(&bar_acc_full[i], 1);
+      tc::mbar_init(&bar_acc_empty[i], 8);
+    }
+    tc::mbar_init(&bar_b_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp >= EPI_WARP0) {
+    int* shist = reinterpret_cast<int*>(smem + L.hist);
+    for (int k = tid - EPI_WARP0 * 32; k < K; k += (NUM_WARPS - EPI_WARP0) * 32) shist[k] = 0;
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  volatile int* errw = &serr;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&bar_b_full, L.bimg_bytes);
+      for (uint32_t off = 0; off < L.bimg_bytes; off += 16384) {
+        const uint32_t n = min(16384u, L.bimg_bytes - off);
+        tc::bulk_g2s(smem + L.bimg + off, p.bimg + off, n, &bar_b_full);
+      }
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t tile = blockIdx.x + it * gridDim.x;
+        const int s = (int)(it & 1);
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        if (!tc::mbar_wait(&bar_stage_empty[s], ph ^ 1u, errw, ERR_STAGE_EMPTY)) break;
+        const int64_t row0 = tile * TM;
+        const int rows = (int)min((int64_t)TM, p.N - row0);
+        const uint32_t bytes = (uint32_t)rows * D * 4;
+        tc::mbar_arrive_expect_tx(&bar_stage_full[s], bytes);
+        tc::bulk_g2s(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      bool ok = tc::mbar_wait(&bar_b_full, 0, errw, ERR_B_FULL);
+      const uint32_t b_lbo = (uint32_t)K * 16, b_sbo = 128;
+      const uint32_t a_lbo = A_CHUNK_BYTES, a_sbo = 128;
+      const uint32_t b_base = tc::smem_u32(smem + L.bimg);
+      uint32_t q = 0;
+      for (int64_t it = 0; ok && it < my_tiles; ++it) {
+        const int a = (int)(it & 1);
+        if (!tc::mbar_wait(&bar_a_full[a], (uint32_t)((it >> 1) & 1), errw, ERR_A_FULL)) break;
+        tc::tc_fence_after();
+        const uint32_t a_base = tc::smem_u32(smem + L.a_img[a]);
+        for (int c = 0; c < nchunks; ++c, ++q) {
+          const uint32_t t = q & 1u;
+          if (!tc::mbar_wait(&bar_acc_empty[t], ((q >> 1) & 1u) ^ 1u, errw, ERR_ACC_EMPTY)) { ok = false; break; }
+          tc::tc_fence_after();
+          const int n = min(256, K - c * 256);
+          const uint32_t idesc = tc::make_idesc_f16(128, n, 0);
+          const uint32_t d_tmem = tmem_base + t * 256u;
+          const uint32_t bc = b_base + (uint32_t)c * 256u * 16u;
+          uint32_t acc = 0;
+          for (int j = 0; j < nk; ++j) {   // zh . eh
+            tc::umma_f16(d_tmem, tc::make_smem_desc(a_base + (uint32_t)j * 2u * a_lbo, a_lbo, a_sbo),
+                         tc::make_smem_desc(bc + (uint32_t)j * 2u * b_lbo, b_lbo, b_sbo), idesc, acc);
+            acc = 1;
+          }
+          for (int j = 0; j < nk; ++j)     // zl . eh
+            tc::umma_f16(d_tmem, tc::make_smem_desc(a_base + (uint32_t)(nk + j) * 2u * a_lbo, a_lbo, a_sbo),
+                         tc::make_smem_desc(bc + (uint32_t)j * 2u * b_lbo, b_lbo, b_sbo), idesc, 1);
+          tc::umma_f16(d_tmem, tc::make_smem_desc(a_base + (uint32_t)(2 * nk) * 2u * a_lbo, a_lbo, a_sbo),
+                       tc::make_smem_desc(bc + (uint32_t)nk * 2u * b_lbo, b_lbo, b_sbo), idesc, 1);   // fold
+          tc::umma_commit(&bar_acc_full[t]);
+        }
+        tc::umma_commit(&bar_a_empty[a]);
+      }
+    }
+  } else if (warp < EPI_WARP0) {
+    // ===================== converters: thread <-> tile row =====================
+    const int r = (warp - CONV_WARP0) * 32 + lane;
+    const CbMeta cb = *p.cb;
+    const int nv = D / 4;   // float4 per row
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int s = (int)(it & 1), a = (int)(it & 1);
+      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      const int rows = (int)min((int64_t)TM, p.N - tile * TM);
+      if (!warp_wait(&bar_stage_full[s], ph, errw, ERR_STAGE_FULL)) break;
+      const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nv;
+      // pass 1: squared norm (lane-rotated chunk order: conflict-free 128-bit reads)
+      float nsq = 0.f;
+      bool finite = true;
+      if (r < rows) {
+        for (int i = 0; i < nv; ++i) {
+          const int c4 = (i + lane) % nv;
+          const float4 v = src[c4];
+          nsq = fmaf(v.x, v.x, nsq); nsq = fmaf(v.y, v.y, nsq); nsq = fmaf(v.z, v.z, nsq); nsq = fmaf(v.w, v.w, nsq);
+        }
+        finite = (nsq < 1e30f);   // false for inf / nan too
+      }
+      // scales and bounds
+      const float zn = sqrtf(nsq) * (1.f + 1e-6f);
+      const bool tiny = !(nsq > 1e-30f);
+      int ex = (int)((__float_as_uint(zn) >> 23) & 255u) - 127;         // zn in [2^ex, 2^(ex+1))
+      float s_n = exp2f((float)(10 - ex));                              // s_n*zn in [2^10, 2^11)
+      const int rexp = cb.half_E - ex + 8;                              // fold scale r_n*2^8 = 2^rexp
+      bool degenerate = (r < rows) && (tiny || !finite || cb.degenerate || rexp > 15 || rexp < -14);
+      if (degenerate || r >= rows) s_n = 0.f;
+      const float zs = s_n * zn;                                        // scaled norm bound
+      const float f0a = __half2float(__float2half_ru(2.f * zs * (1.f + 1.f / 128.f)));
+      const float fr = (s_n == 0.f) ? 0.f : exp2f((float)rexp);
+      const float bias2 = 2.f * f0a * cb.b0;
+      const float eps = zs * cb.delta_max * (1.f + 1.f / 64.f)
+                      + (zs * (1.f / 4194304.f) + sqrtf((float)D) * (1.f / 33554432.f)) * cb.eh_norm_bound
+                      + bias2 * ((float)(2 * nk + 3) * (1.f / 1048576.f))      // tensor-core FP32 accumulation
+                      + bias2 * (1.f / 262144.f)                               // 5 packed index bits
+                      + 16.f * fr * (1.f / 256.f);                             // ee rounding (r_n = fr / 256)
+      float band = 2.f * eps * (1.f + 1.f / 16.f);
+      if (degenerate) band = -1.f;    // marks "send to the exact kernel"
+      if (!warp_wait(&bar_a_empty[a], ph ^ 1u, errw, ERR_A_EMPTY)) break;
+      // pass 2: convert and write the A image
+      uint8_t* aimg = smem + L.a_img[a] + (r >> 3) * 128 + (r & 7) * 16;
+      for (int i = 0; i < nv / 2; ++i) {
+        const int c8 = (i + lane) % (nv / 2);                           // 8-wide k-chunk
+        const float4 v0 = src[2 * c8], v1 = src[2 * c8 + 1];
+        const float x[8] = {v0.x * s_n, v0.y * s_n, v0.z * s_n, v0.w * s_n, v1.x * s_n, v1.y * s_n, v1.z * s_n, v1.w * s_n};
+        __half2 hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hi[e] = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+          const float2 hf = __half22float2(hi[e]);
+          lo[e] = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+        }
+        *reinterpret_cast<uint4*>(aimg + (size_t)c8 * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(aimg + (size_t)(nv / 2 + c8) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(lo);
+      }
+      {
+        __half2 f[4];
+        f[0] = __floats2half2_rn(f0a, fr);
+        f[1] = __floats2half2_rn(fr, fr);
+        f[2] = __floats2half2_rn(0.f, 0.f);
+        f[3] = f[2];
+        *reinterpret_cast<uint4*>(aimg + (size_t)(nv) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
+        f[0] = f[2]; f[1] = f[2];
+        *reinterpret_cast<uint4*>(aimg + (size_t)(nv + 1) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
+      }
+      reinterpret_cast<float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r] = band;
+      tc::mbar_arrive(&bar_stage_empty[s]);   // staging slot may be refilled
+      tc::fence_proxy_async_smem();           // A image visible to the tensor core (async proxy)
+      tc::mbar_arrive(&bar_a_full[a]);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int w = warp - EPI_WARP0;
+    const int quarter = warp & 3;       // TMEM lanes this warp may access: 32*(warp_id % 4)
+    const int half = w >> 2;            // which sub-chunks of each accumulator chunk
+    const int r = quarter * 32 + lane;  // tile row == TMEM lane
+    const int etid = tid - EPI_WARP0 * 32;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    float* fin_key = reinterpret_cast<float*>(smem + L.fin);
+    int* fin_col = reinterpret_cast<int*>(smem + L.fin + 2 * TM * 4);
+    float* fin_cnt = reinterpret_cast<float*>(smem + L.fin + 4 * TM * 4);
+    int* sidx = reinterpret_cast<int*>(smem + L.sidx);
+    int* shist = reinterpret_cast<int*>(smem + L.hist);
+    const float BIG = 1048576.f;
+    const uint32_t mask = p.index_mask;
+    double sse_acc = 0.0;
+    uint32_t q = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t row0 = tile * TM;
+      const int rows = (int)min((int64_t)TM, p.N - row0);
+      float m1 = __uint_as_float(0x7f800000u), cnt = 0.f, band = 0.f;
+      int best_col = 0;
+      bool ok = true;
+      for (int c = 0; c < nchunks; ++c, ++q) {
+        const uint32_t t = q & 1u;
+        if (ok) ok = warp_wait(&bar_acc_full[t], (q >> 1) & 1u, errw, ERR_ACC_FULL);
+        if (!ok) continue;
+        tc::tc_fence_after();
+        if (c == 0) band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
+        const int n = min(256, K - c * 256);
+        for (int sc = half; sc * 32 < n; sc += 2) {
+          uint32_t v[32];
+          tc::tmem_ld32(tmem_base + lane_addr + t * 256u + (uint32_t)sc * 32u, v);
+          tc::tmem_ld_wait();
+          float key[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(pack_key(v[j], mask, (uint32_t)j));
+          // sub-chunk minimum: FMNMX3 tree (ALU pipe)
+          float a0 = min3f(key[0], key[1], key[2]), a1 = min3f(key[3], key[4], key[5]);
+          float a2 = min3f(key[6], key[7], key[8]), a3 = min3f(key[9], key[10], key[11]);
+          float a4 = min3f(key[12], key[13], key[14]), a5 = min3f(key[15], key[16], key[17]);
+          float a6 = min3f(key[18], key[19], key[20]), a7 = min3f(key[21], key[22], key[23]);
+          float a8 = min3f(key[24], key[25], key[26]), a9 = min3f(key[27], key[28], key[29]);
+          a0 = min3f(a0, a1, a2); a3 = min3f(a3, a4, a5); a6 = min3f(a6, a7, a8); a9 = min3f(a9, key[30], key[31]);
+          const float m = fminf(min3f(a0, a3, a6), a9);
+          // running minimum; cnt = number of OTHER keys within the band of the minimum (a superset).
+          // An improvement by more than the band voids every earlier key exactly (cnt := -1 cancels
+          // the new minimum's own hit below); a smaller improvement leaves the old minimum in the band,
+          // which the new minimum's own hit accounts for.
+          if (m < m1) {
+            if (m1 - m > band) cnt = -1.f;
+            m1 = m;
+            best_col = c * 256 + sc * 32 + (int)(__float_as_uint(m) & 31u);
+          }
+          // count keys < m1 + band on the FMA pipe: fma.sat((T - key) * BIG) is exactly 0 or 1
+          const float TB = (m1 + band) * BIG;
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            c0 += fma_sat(key[j + 0], -BIG, TB);
+            c1 += fma_sat(key[j + 1], -BIG, TB);
+            c2 += fma_sat(key[j + 2], -BIG, TB);
+            c3 += fma_sat(key[j + 3], -BIG, TB);
+          }
+          cnt += (c0 + c1) + (c2 + c3);
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_acc_empty[t]);
+      }
+      // ---- combine the two column halves of each row (barrier doubles as error consensus) ----
+      fin_key[half * TM + r] = m1;
+      fin_col[half * TM + r] = best_col;
+      fin_cnt[half * TM + r] = cnt;
+      if (!named_bar_and(1, 256, ok)) break;
+      if (half == 0) {
+        const float ko = fin_key[TM + r];
+        const int co = fin_col[TM + r];
+        const float no = fin_cnt[TM + r];
+        bool flag;
+        int col;
+        if (ko < m1) { col = co; flag = (no > 0.5f) || (m1 - ko <= band); }
+        else         { col = best_col; flag = (cnt > 0.5f) || (ko - m1 <= band); }
+        if (band < 0.f) flag = true;
+        const bool valid = r < rows;
+        flag = flag && valid;
+        sidx[r] = flag ? -1 : col;
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(p.counters, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (flag) p.row_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)(row0 + r);
+        }
+      }
+      named_bar_sync(1, 256);
+      // ---- gather / straight-through / SSE / histogram for the decided rows (16 rows per warp) ----
+      float lsse = 0.f;
+      {
+        const int sub = lane >> 4, l16 = lane & 15;
+        for (int i = 0; i < 8; ++i) {
+          const int rr = w * 16 + i * 2 + sub;
+          const int k = sidx[rr];
+          if (rr < rows && k >= 0) {
+            const float* erow = p.E + (int64_t)k * D;
+            const float* zrow = p.z + (row0 + rr) * D;
+            float* orow = p.zq + (row0 + rr) * D;
+            for (int cc = l16 * 4; cc < D; cc += 64) {
+              const float4 e4 = ldg4(erow + cc);
+              float4 o4 = e4;
+              if (p.train) {
+                const float4 z4 = ldg4(zrow + cc);
+                const float dx = __fsub_rn(e4.x, z4.x), dy = __fsub_rn(e4.y, z4.y);
+                const float dz = __fsub_rn(e4.z, z4.z), dw = __fsub_rn(e4.w, z4.w);
+                lsse = fmaf(dx, dx, lsse); lsse = fmaf(dy, dy, lsse); lsse = fmaf(dz, dz, lsse); lsse = fmaf(dw, dw, lsse);
+                o4 = make_float4(__fadd_rn(z4.x, dx), __fadd_rn(z4.y, dy), __fadd_rn(z4.z, dz), __fadd_rn(z4.w, dw));
+              }
+              *reinterpret_cast<float4*>(orow + cc) = o4;
+            }
+            if (l16 == 0) {
+              p.idx[row0 + rr] = (int64_t)k;
+              if (p.train) atomicAdd(&shist[k], 1);
+            }
+          }
+        }
+      }
+      sse_acc += (double)lsse;
+      named_bar_sync(1, 256);   // fin / sidx are rewritten by the next tile
+      (void)etid;
+    }
+    // ---- CTA totals ----
+    if (p.train) {
+      named_bar_sync(1, 256);
+      for (int k = etid; k < K; k += 256) {
+        const int hcount = shist[k];
+        if (hcount) atomicAdd(p.hist + k, (unsigned long long)hcount);
+      }
+      sse_acc = warp_sum(sse_acc);
+      if (lane == 0 && sse_acc != 0.0) atomicAdd(p.sse, sse_acc);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (tid == 0 && serr) atomicExch(p.counters + 1, serr);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+bool vq_tc_supported(int64_t N, int K, int D) {
+  if (N <= 0 || N > 2147483647LL - 256) return false;
+  if (D % 16 != 0 || D < 16 || D > 256) return false;
+  if (K % 32 != 0 || K < 32 || K > 4096) return false;
+  return smem_layout(K, D).total + 2048 <= 227 * 1024;
+}
+
+size_t vq_tc_operand_bytes(int K, int D) {
+  return align_up(sizeof(CbMeta), 256) + align_up((size_t)smem_layout(K, D).bimg_bytes, 256);
+}
+
+int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,
+                 int64_t* idx, unsigned long long* hist, double* sse, void* bop, int* counters, int* row_list,
+                 cudaStream_t s) {
+  DeviceProps dp;
+  int rc = device_props(&dp);
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(E) | reinterpret_cast<uintptr_t>(z_q)) % 16 != 0)
+    return fail(DVQ_ERR_BAD_ALIGN, "tcgen05 path needs 16-byte aligned z / E / z_q");
+  CbMeta* cb = static_cast<CbMeta*>(bop);
+  uint8_t* bimg = static_cast<uint8_t*>(bop) + align_up(sizeof(CbMeta), 256);
+  const SmemLayout L = smem_layout(K, D);
+  tc_cb_stats_kernel<<<1, 256, 0, s>>>(ee, K, cb, counters);
+  DVQ_CUDA_CHECK(cudaGetLastError());
+  DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, L.bimg_bytes, s));
+  tc_cb_image_kernel<<<(K * 32 + 255) / 256, 256, 0, s>>>(E, ee, K, D, cb, bimg);
+  DVQ_CUDA_CHECK(cudaGetLastError());
+  count_launch(2);
+
+  TcParams p;
+  p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.N = N; p.K = K; p.D = D; p.train = train;
+  p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list;
+  p.index_mask = 0xffffffe0u;
+  p.ntiles = (N + TM - 1) / TM;
+  const size_t smem = L.total + 1024;
+  DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = p.ntiles < dp.sm_count ? p.ntiles : dp.sm_count;
+  vq_tc_kernel<<<(unsigned)grid, NTHREADS, smem, s>>>(p);
+  DVQ_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return DVQ_OK;
+}
+
 }  // namespace dvq

@@ -35,6 +35,7 @@ SYMBOLS = {
     "dvq_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dvq_vq_workspace_bytes": (_i, [_i64, _i, _i, _i, C.POINTER(_sz)]),
     "dvq_vq_forward": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dvq_vq_read_counters": (_i, [_vp, _i64, _i, _i, _i, C.POINTER(_i)]),
     "dvq_vq_finalize": (_i, [_vp, _vp, _i64, _i, _i, _f, _f, _vp, _vp, _vp]),
     "dvq_gather": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "dvq_onehot": (_i, [_vp, _i64, _i, _vp, _vp]),

@@ -143,6 +143,18 @@ class VectorQuantizer(nn.Module):
                 z_q.data_ptr(), idx.data_ptr(), onehot.data_ptr() if onehot is not None else None,
                 hist_ptr, sse_ptr, ws.data_ptr(), ws.numel(), _stream_ptr(z.device)), "dvq_vq_forward")
 
+    def last_counters(self, n: int, flags: int | None = None):
+        """(rows refined by the exact FP32 kernel, tcgen05 pipeline error code) of the last forward
+        over ``n`` rows — a synchronous diagnostic read, not part of the hot path."""
+        import ctypes as C
+        if self._ws is None:
+            return 0, 0
+        out = (C.c_int * 4)()
+        with torch.cuda.device(self._ws.device):
+            _cabi.check(_cabi.lib.dvq_vq_read_counters(self._ws.data_ptr(), n, self.n_e, self.e_dim,
+                                                       self.path if flags is None else flags, out), "dvq_vq_read_counters")
+        return int(out[0]), int(out[1])
+
     def _forward_train_raw(self, z, weight):
         n = z.numel() // self.e_dim
         dev = z.device

@@ -91,6 +91,11 @@ DVQ_API int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int
                    unsigned long long* hist, double* sse,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostics of the last dvq_vq_forward that used `workspace` (synchronous device->host read):
+ * out[0] = rows the tensor-core filter sent to the exact FP32 kernel, out[1] = pipeline protocol
+ * error code of the tcgen05 kernel (0 = none), out[2..3] reserved.  Zeros on the FP32-only path. */
+DVQ_API int dvq_vq_read_counters(const void* workspace, int64_t N, int K, int D, int flags, int* out4);
+
 /* loss = al*mean((z_q-z)^2) + beta*mean((z_q-z)^2) (quantizer.py:56-57),
  * perplexity = exp(-sum p log(p+1e-10)), p = hist/N_total (:63-64). */
 DVQ_API int dvq_vq_finalize(const unsigned long long* hist, const double* sse, int64_t N_total, int K, int D,
