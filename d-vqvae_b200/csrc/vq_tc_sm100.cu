@@ -20,12 +20,12 @@
 // minimum; the count of such keys is kept with a running (never too small) threshold, exact
 // resets, and FFMA.SAT arithmetic on the FMA pipe.  Undecided rows (a few %) go to the list.
 //
-// Pipeline (one persistent CTA per SM, 14 warps):
+// Pipeline (one persistent CTA per SM, 16 warps):
 //   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B)
 //   warp 1      MMA      : single elected thread issues tcgen05.mma, commits to mbarriers
 //   warps 2-5   convert  : staging -> registers -> scales / norms / bounds -> FP16 A image (2 stages)
-//   warps 6-13  epilogue : tcgen05.ld TMEM -> keys -> argmin + ambiguity count; then gather
-//                          E[idx] (128-bit), z_q, SSE, smem histogram, idx (int64)
+//   warps 6-13  epilogue : tcgen05.ld TMEM (software-pipelined) -> keys -> argmin + ambiguity count
+//   warps 14-15 gather   : E[idx] (128-bit, 8-16 loads in flight per lane), z_q, SSE, smem histogram, idx
 // TMEM: 512 columns = 2 accumulator stages of 256, so the MMA of one 256-code chunk overlaps the
 // epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays resident in
 // shared memory for the life of the CTA.
@@ -39,13 +39,15 @@ namespace {
 
 constexpr int TM = 128;                 // rows per tile
 constexpr int A_CHUNK_BYTES = TM * 16 + 32;  // one 8-wide k-chunk of the A image (+32 B: bank spreading)
-constexpr int NUM_WARPS = 14;
-constexpr int NTHREADS = NUM_WARPS * 32;
-constexpr int EPI_WARP0 = 6;
 constexpr int CONV_WARP0 = 2;
+constexpr int EPI_WARP0 = 6;
+constexpr int GATHER_WARP0 = 14;
+constexpr int GATHER_WARPS = 2;
+constexpr int NUM_WARPS = GATHER_WARP0 + GATHER_WARPS;
+constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int META_SLOTS = 4;
 
-enum ErrCode { ERR_STAGE_FULL = 1, ERR_STAGE_EMPTY, ERR_A_FULL, ERR_A_EMPTY, ERR_ACC_FULL, ERR_ACC_EMPTY, ERR_B_FULL };
+enum ErrCode { ERR_STAGE_FULL = 1, ERR_STAGE_EMPTY, ERR_A_FULL, ERR_A_EMPTY, ERR_ACC_FULL, ERR_ACC_EMPTY, ERR_B_FULL, ERR_FIN, ERR_SIDX };
 
 struct CbMeta {          // written by the prep kernels, read by the main kernel
   float s_E;             // power-of-two codebook scale
@@ -91,8 +93,8 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   L.stage[0] = off; off += L.stage_bytes;
   L.stage[1] = off; off += L.stage_bytes;
   L.meta = off; off += META_SLOTS * TM * 4;
-  L.fin = off; off += 2 * TM * 12;      // per half: key, col, cnt
-  L.sidx = off; off += TM * 4;
+  L.fin = off; off += 2 * TM * 12;      // 2 slots of (key, col, cnt) from the half-1 warps
+  L.sidx = off; off += 2 * TM * 4;      // 2 slots of final code index (-1: undecided)
   L.hist = off; off += (uint32_t)K * 4;
   L.total = off;
   return L;
@@ -182,21 +184,16 @@ __device__ __forceinline__ uint32_t pack_key(uint32_t v, uint32_t mask, uint32_t
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(v), "r"(mask), "r"(j));   // (v & mask) | j
   return r;
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// barrier + AND-reduction of a predicate over the participating threads (error consensus)
-__device__ __forceinline__ bool named_bar_and(int id, int nthreads, bool pred) {
-  uint32_t r;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 q, %3, 0;\n\t"
-      "bar.red.and.pred p, %1, %2, q;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(r)
-      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
-      : "memory");
-  return r != 0;
+// tcgen05.wait::ld that also carries a register dependence on the loaded values, so the compiler
+// cannot move their consumers above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 // whole-warp wait: lane 0 spins (bounded), then every lane performs its own (now immediate) acquire
 __device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volatile int* errw, int code) {
@@ -209,10 +206,55 @@ __device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volati
   __syncwarp();
   return ok != 0;
 }
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {   // one arrival per warp, after all lanes are done
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) tc::mbar_arrive(bar);
+}
+
+struct RowState {   // per (row, column-half) running result of the filter
+  float m1;         // smallest key so far (index in the 5 low bits)
+  float cnt;        // number of OTHER keys within `band` of m1 (a superset count)
+  int col;          // global code index of m1
+};
+
+// One 32-column sub-chunk: keys -> FMNMX3 tree -> running minimum with exact reset -> count of keys
+// inside the band on the FMA pipe (fma.sat((T - key) * BIG) is exactly 0 or 1).
+__device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], uint32_t mask, int col0, float band, RowState& st) {
+  const float BIG = 1048576.f;
+  float key[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(pack_key(v[j], mask, (uint32_t)j));
+  float a0 = min3f(key[0], key[1], key[2]), a1 = min3f(key[3], key[4], key[5]);
+  float a2 = min3f(key[6], key[7], key[8]), a3 = min3f(key[9], key[10], key[11]);
+  float a4 = min3f(key[12], key[13], key[14]), a5 = min3f(key[15], key[16], key[17]);
+  float a6 = min3f(key[18], key[19], key[20]), a7 = min3f(key[21], key[22], key[23]);
+  float a8 = min3f(key[24], key[25], key[26]), a9 = min3f(key[27], key[28], key[29]);
+  a0 = min3f(a0, a1, a2); a3 = min3f(a3, a4, a5); a6 = min3f(a6, a7, a8); a9 = min3f(a9, key[30], key[31]);
+  const float m = fminf(min3f(a0, a3, a6), a9);
+  // An improvement by more than the band voids every earlier key exactly (cnt := -1 cancels the new
+  // minimum's own hit below); a smaller improvement leaves the old minimum inside the band, which the
+  // new minimum's own hit accounts for.
+  if (m < st.m1) {
+    if (st.m1 - m > band) st.cnt = -1.f;
+    st.m1 = m;
+    st.col = col0 + (int)(__float_as_uint(m) & 31u);
+  }
+  const float TB = (st.m1 + band) * BIG;
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    c0 += fma_sat(key[j + 0], -BIG, TB);
+    c1 += fma_sat(key[j + 1], -BIG, TB);
+    c2 += fma_sat(key[j + 2], -BIG, TB);
+    c3 += fma_sat(key[j + 3], -BIG, TB);
+  }
+  st.cnt += (c0 + c1) + (c2 + c3);
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_stage_full[2], bar_stage_empty[2], bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2], bar_b_full;
+  __shared__ uint64_t bar_fin_full[2], bar_fin_empty[2], bar_sidx_full[2], bar_sidx_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int serr;
 
@@ -227,18 +269,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     serr = 0;
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&bar_stage_full[i], 1);
-      tc::mbar_init(&bar_stage_empty[i], 128);
-      tc::mbar_init(&bar_a_full[i], 128);
+      tc::mbar_init(&bar_stage_empty[i], 4);    // one arrival per converter warp
+      tc::mbar_init(&bar_a_full[i], 128);       // every converter thread (after its own proxy fence)
       tc::mbar_init(&bar_a_empty[i], 1);
       tc::mbar_init(&bar_acc_full[i], 1);
-      tc::mbar_init(&bar_acc_empty[i], 8);
+      tc::mbar_init(&bar_acc_empty[i], 8);      // one arrival per epilogue warp
+      tc::mbar_init(&bar_fin_full[i], 4);       // half-1 epilogue warps -> half-0
+      tc::mbar_init(&bar_fin_empty[i], 4);
+      tc::mbar_init(&bar_sidx_full[i], 4);      // half-0 epilogue warps -> gather warps
+      tc::mbar_init(&bar_sidx_empty[i], GATHER_WARPS);
     }
     tc::mbar_init(&bar_b_full, 1);
     tc::fence_barrier_init();
   }
-  if (warp >= EPI_WARP0) {
+  {
     int* shist = reinterpret_cast<int*>(smem + L.hist);
-    for (int k = tid - EPI_WARP0 * 32; k < K; k += (NUM_WARPS - EPI_WARP0) * 32) shist[k] = 0;
+    for (int k = tid; k < K; k += NTHREADS) shist[k] = 0;
   }
   if (warp == 1) tc::tmem_alloc(&tmem_slot, 512);
   tc::tc_fence_before();
@@ -374,33 +420,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         *reinterpret_cast<uint4*>(aimg + (size_t)(nv + 1) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
       }
       reinterpret_cast<float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r] = band;
-      tc::mbar_arrive(&bar_stage_empty[s]);   // staging slot may be refilled
+      warp_arrive(&bar_stage_empty[s]);       // staging slot may be refilled
       tc::fence_proxy_async_smem();           // A image visible to the tensor core (async proxy)
       tc::mbar_arrive(&bar_a_full[a]);
     }
-  } else {
-    // ===================== epilogue =====================
+  } else if (warp < GATHER_WARP0) {
+    // ===================== epilogue: TMEM -> (min, ambiguity) per row =====================
     const int w = warp - EPI_WARP0;
     const int quarter = warp & 3;       // TMEM lanes this warp may access: 32*(warp_id % 4)
     const int half = w >> 2;            // which sub-chunks of each accumulator chunk
     const int r = quarter * 32 + lane;  // tile row == TMEM lane
-    const int etid = tid - EPI_WARP0 * 32;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    float* fin_key = reinterpret_cast<float*>(smem + L.fin);
-    int* fin_col = reinterpret_cast<int*>(smem + L.fin + 2 * TM * 4);
-    float* fin_cnt = reinterpret_cast<float*>(smem + L.fin + 4 * TM * 4);
-    int* sidx = reinterpret_cast<int*>(smem + L.sidx);
-    int* shist = reinterpret_cast<int*>(smem + L.hist);
-    const float BIG = 1048576.f;
     const uint32_t mask = p.index_mask;
-    double sse_acc = 0.0;
     uint32_t q = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t row0 = tile * TM;
       const int rows = (int)min((int64_t)TM, p.N - row0);
-      float m1 = __uint_as_float(0x7f800000u), cnt = 0.f, band = 0.f;
-      int best_col = 0;
+      const int slot = (int)(it & 1);
+      const uint32_t sph = (uint32_t)((it >> 1) & 1);
+      RowState st;
+      st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0.f; st.col = 0;
+      float band = 0.f;
       bool ok = true;
       for (int c = 0; c < nchunks; ++c, ++q) {
         const uint32_t t = q & 1u;
@@ -409,63 +450,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         tc::tc_fence_after();
         if (c == 0) band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
         const int n = min(256, K - c * 256);
-        for (int sc = half; sc * 32 < n; sc += 2) {
-          uint32_t v[32];
-          tc::tmem_ld32(tmem_base + lane_addr + t * 256u + (uint32_t)sc * 32u, v);
-          tc::tmem_ld_wait();
-          float key[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(pack_key(v[j], mask, (uint32_t)j));
-          // sub-chunk minimum: FMNMX3 tree (ALU pipe)
-          float a0 = min3f(key[0], key[1], key[2]), a1 = min3f(key[3], key[4], key[5]);
-          float a2 = min3f(key[6], key[7], key[8]), a3 = min3f(key[9], key[10], key[11]);
-          float a4 = min3f(key[12], key[13], key[14]), a5 = min3f(key[15], key[16], key[17]);
-          float a6 = min3f(key[18], key[19], key[20]), a7 = min3f(key[21], key[22], key[23]);
-          float a8 = min3f(key[24], key[25], key[26]), a9 = min3f(key[27], key[28], key[29]);
-          a0 = min3f(a0, a1, a2); a3 = min3f(a3, a4, a5); a6 = min3f(a6, a7, a8); a9 = min3f(a9, key[30], key[31]);
-          const float m = fminf(min3f(a0, a3, a6), a9);
-          // running minimum; cnt = number of OTHER keys within the band of the minimum (a superset).
-          // An improvement by more than the band voids every earlier key exactly (cnt := -1 cancels
-          // the new minimum's own hit below); a smaller improvement leaves the old minimum in the band,
-          // which the new minimum's own hit accounts for.
-          if (m < m1) {
-            if (m1 - m > band) cnt = -1.f;
-            m1 = m;
-            best_col = c * 256 + sc * 32 + (int)(__float_as_uint(m) & 31u);
+        const uint32_t tbase = tmem_base + lane_addr + t * 256u;
+        if (n == 256) {
+          // 4 sub-chunks per warp, software-pipelined: the next TMEM load is in flight while this one is reduced
+          uint32_t va[32], vb[32];
+          tc::tmem_ld32(tbase + (uint32_t)(half + 0) * 32u, va);
+          tmem_ld_wait_dep(va);
+          tc::tmem_ld32(tbase + (uint32_t)(half + 2) * 32u, vb);
+          filter_subchunk(va, mask, c * 256 + (half + 0) * 32, band, st);
+          tmem_ld_wait_dep(vb);
+          tc::tmem_ld32(tbase + (uint32_t)(half + 4) * 32u, va);
+          filter_subchunk(vb, mask, c * 256 + (half + 2) * 32, band, st);
+          tmem_ld_wait_dep(va);
+          tc::tmem_ld32(tbase + (uint32_t)(half + 6) * 32u, vb);
+          filter_subchunk(va, mask, c * 256 + (half + 4) * 32, band, st);
+          tmem_ld_wait_dep(vb);
+          filter_subchunk(vb, mask, c * 256 + (half + 6) * 32, band, st);
+        } else {
+          for (int sc = half; sc * 32 < n; sc += 2) {
+            uint32_t v[32];
+            tc::tmem_ld32(tbase + (uint32_t)sc * 32u, v);
+            tmem_ld_wait_dep(v);
+            filter_subchunk(v, mask, c * 256 + sc * 32, band, st);
           }
-          // count keys < m1 + band on the FMA pipe: fma.sat((T - key) * BIG) is exactly 0 or 1
-          const float TB = (m1 + band) * BIG;
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            c0 += fma_sat(key[j + 0], -BIG, TB);
-            c1 += fma_sat(key[j + 1], -BIG, TB);
-            c2 += fma_sat(key[j + 2], -BIG, TB);
-            c3 += fma_sat(key[j + 3], -BIG, TB);
-          }
-          cnt += (c0 + c1) + (c2 + c3);
         }
         tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&bar_acc_empty[t]);
+        warp_arrive(&bar_acc_empty[t]);
       }
-      // ---- combine the two column halves of each row (barrier doubles as error consensus) ----
-      fin_key[half * TM + r] = m1;
-      fin_col[half * TM + r] = best_col;
-      fin_cnt[half * TM + r] = cnt;
-      if (!named_bar_and(1, 256, ok)) break;
-      if (half == 0) {
-        const float ko = fin_key[TM + r];
-        const int co = fin_col[TM + r];
-        const float no = fin_cnt[TM + r];
+      if (*errw) break;
+      float* fin_key = reinterpret_cast<float*>(smem + L.fin) + slot * 3 * TM;
+      int* fin_col = reinterpret_cast<int*>(fin_key + TM);
+      float* fin_cnt = fin_key + 2 * TM;
+      if (half == 1) {
+        // hand this half's result to the half-0 warp that owns the same rows
+        if (!warp_wait(&bar_fin_empty[slot], sph ^ 1u, errw, ERR_FIN)) break;
+        fin_key[r] = st.m1; fin_col[r] = st.col; fin_cnt[r] = st.cnt;
+        warp_arrive(&bar_fin_full[slot]);
+      } else {
+        if (!warp_wait(&bar_fin_full[slot], sph, errw, ERR_FIN)) break;
+        const float ko = fin_key[r];
+        const int co = fin_col[r];
+        const float no = fin_cnt[r];
+        warp_arrive(&bar_fin_empty[slot]);
         bool flag;
         int col;
-        if (ko < m1) { col = co; flag = (no > 0.5f) || (m1 - ko <= band); }
-        else         { col = best_col; flag = (cnt > 0.5f) || (ko - m1 <= band); }
+        if (ko < st.m1) { col = co; flag = (no > 0.5f) || (st.m1 - ko <= band); }
+        else            { col = st.col; flag = (st.cnt > 0.5f) || (ko - st.m1 <= band); }
         if (band < 0.f) flag = true;
-        const bool valid = r < rows;
-        flag = flag && valid;
-        sidx[r] = flag ? -1 : col;
+        flag = flag && (r < rows);
+        if (!warp_wait(&bar_sidx_empty[slot], sph ^ 1u, errw, ERR_SIDX)) break;
+        reinterpret_cast<int*>(smem + L.sidx)[slot * TM + r] = flag ? -1 : col;
+        warp_arrive(&bar_sidx_full[slot]);
+        // undecided rows -> list for the exact FP32 kernel (one atomic per warp that has any)
         const unsigned bal = __ballot_sync(0xffffffffu, flag);
         if (bal) {
           int base = 0;
@@ -474,45 +510,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           if (flag) p.row_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)(row0 + r);
         }
       }
-      named_bar_sync(1, 256);
-      // ---- gather / straight-through / SSE / histogram for the decided rows (16 rows per warp) ----
+    }
+  } else {
+    // ===================== gather: z_q, idx, SSE, histogram for the decided rows =====================
+    const int gw = warp - GATHER_WARP0;
+    int* shist = reinterpret_cast<int*>(smem + L.hist);
+    const int nv = D / 4;                              // float4 slots per row
+    const int rows_per_warp = TM / GATHER_WARPS;
+    const int slots = rows_per_warp * nv;              // float4 slots this warp owns per tile
+    double sse_acc = 0.0;
+    constexpr int U = 8;                               // loads in flight per lane (x2 in train mode)
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t row0 = tile * TM;
+      const int rows = (int)min((int64_t)TM, p.N - row0);
+      const int slot = (int)(it & 1);
+      const uint32_t sph = (uint32_t)((it >> 1) & 1);
+      if (!warp_wait(&bar_sidx_full[slot], sph, errw, ERR_SIDX)) break;
+      const int* sidx = reinterpret_cast<const int*>(smem + L.sidx) + slot * TM;
       float lsse = 0.f;
-      {
-        const int sub = lane >> 4, l16 = lane & 15;
-        for (int i = 0; i < 8; ++i) {
-          const int rr = w * 16 + i * 2 + sub;
-          const int k = sidx[rr];
-          if (rr < rows && k >= 0) {
-            const float* erow = p.E + (int64_t)k * D;
-            const float* zrow = p.z + (row0 + rr) * D;
-            float* orow = p.zq + (row0 + rr) * D;
-            for (int cc = l16 * 4; cc < D; cc += 64) {
-              const float4 e4 = ldg4(erow + cc);
-              float4 o4 = e4;
-              if (p.train) {
-                const float4 z4 = ldg4(zrow + cc);
-                const float dx = __fsub_rn(e4.x, z4.x), dy = __fsub_rn(e4.y, z4.y);
-                const float dz = __fsub_rn(e4.z, z4.z), dw = __fsub_rn(e4.w, z4.w);
-                lsse = fmaf(dx, dx, lsse); lsse = fmaf(dy, dy, lsse); lsse = fmaf(dz, dz, lsse); lsse = fmaf(dw, dw, lsse);
-                o4 = make_float4(__fadd_rn(z4.x, dx), __fadd_rn(z4.y, dy), __fadd_rn(z4.z, dz), __fadd_rn(z4.w, dw));
-              }
-              *reinterpret_cast<float4*>(orow + cc) = o4;
-            }
-            if (l16 == 0) {
-              p.idx[row0 + rr] = (int64_t)k;
-              if (p.train) atomicAdd(&shist[k], 1);
-            }
+      for (int base = 0; base < slots; base += U * 32) {
+        float4 e4[U], z4[U];
+        int kk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int sl = base + u * 32 + lane;
+          const int rr = gw * rows_per_warp + sl / nv;
+          const int c4 = sl - (sl / nv) * nv;
+          int k = -1;
+          if (sl < slots && rr < rows) k = sidx[rr];
+          kk[u] = k;
+          if (k >= 0) {
+            e4[u] = ldg4(p.E + (int64_t)k * D + c4 * 4);
+            if (p.train) z4[u] = ldg4(p.z + (row0 + rr) * D + c4 * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (kk[u] < 0) continue;
+          const int sl = base + u * 32 + lane;
+          const int rr = gw * rows_per_warp + sl / nv;
+          const int c4 = sl - (sl / nv) * nv;
+          float4 o4 = e4[u];
+          if (p.train) {
+            const float dx = __fsub_rn(e4[u].x, z4[u].x), dy = __fsub_rn(e4[u].y, z4[u].y);
+            const float dz = __fsub_rn(e4[u].z, z4[u].z), dw = __fsub_rn(e4[u].w, z4[u].w);
+            lsse = fmaf(dx, dx, lsse); lsse = fmaf(dy, dy, lsse); lsse = fmaf(dz, dz, lsse); lsse = fmaf(dw, dw, lsse);
+            o4 = make_float4(__fadd_rn(z4[u].x, dx), __fadd_rn(z4[u].y, dy), __fadd_rn(z4[u].z, dz), __fadd_rn(z4[u].w, dw));
+          }
+          *reinterpret_cast<float4*>(p.zq + (row0 + rr) * D + c4 * 4) = o4;
+          if (c4 == 0) {
+            p.idx[row0 + rr] = (int64_t)kk[u];
+            if (p.train) atomicAdd(&shist[kk[u]], 1);
           }
         }
       }
+      warp_arrive(&bar_sidx_empty[slot]);
       sse_acc += (double)lsse;
-      named_bar_sync(1, 256);   // fin / sidx are rewritten by the next tile
-      (void)etid;
     }
-    // ---- CTA totals ----
+    // ---- CTA totals (only the gather warps touch shist after the start-up clear) ----
     if (p.train) {
-      named_bar_sync(1, 256);
-      for (int k = etid; k < K; k += 256) {
+      asm volatile("bar.sync 1, %0;" ::"r"(GATHER_WARPS * 32) : "memory");
+      for (int k = tid - GATHER_WARP0 * 32; k < K; k += GATHER_WARPS * 32) {
         const int hcount = shist[k];
         if (hcount) atomicAdd(p.hist + k, (unsigned long long)hcount);
       }
@@ -533,7 +592,7 @@ bool vq_tc_supported(int64_t N, int K, int D) {
   if (N <= 0 || N > 2147483647LL - 256) return false;
   if (D % 16 != 0 || D < 16 || D > 256) return false;
   if (K % 32 != 0 || K < 32 || K > 4096) return false;
-  return smem_layout(K, D).total + 2048 <= 227 * 1024;
+  return smem_layout(K, D).total + 128 + 512 <= 227 * 1024;   // + alignment slack + static barriers
 }
 
 size_t vq_tc_operand_bytes(int K, int D) {
@@ -563,7 +622,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list;
   p.index_mask = 0xffffffe0u;
   p.ntiles = (N + TM - 1) / TM;
-  const size_t smem = L.total + 1024;
+  const size_t smem = L.total + 128;
   DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = p.ntiles < dp.sm_count ? p.ntiles : dp.sm_count;
   vq_tc_kernel<<<(unsigned)grid, NTHREADS, smem, s>>>(p);
