@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "dvq", "libdvq_sm100.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-         "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+         "-I", os.path.join(ROOT, "include"), "-I", CSRC] + (["-DDVQ_TC_STATS"] if os.environ.get("DVQ_TC_STATS") else [])
 
 
 def _sources():

@@ -80,7 +80,7 @@ VqWorkspace vq_workspace_layout(int64_t N, int K, int D, int flags) {
   w.off_ee = off;
   off = align_up(off + sizeof(float) * (size_t)K, 256);
   w.off_counters = off;
-  off = align_up(off + sizeof(int) * 8, 256);
+  off = align_up(off + sizeof(int) * 64, 256);   // [0..7] counters, [8..63] optional wait-time stats
   const bool may_tc = (flags & DVQ_PATH_MASK) != DVQ_PATH_SIMT && vq_tc_supported(N, K, D);
   w.off_rowlist = off;
   if (may_tc) off = align_up(off + sizeof(int) * (size_t)N, 256);
@@ -222,6 +222,15 @@ int dvq_vq_read_counters(const void* workspace, int64_t N, int K, int D, int fla
   if (!use_tc) return DVQ_OK;
   const VqWorkspace w = vq_workspace_layout(N, K, D, flags);
   DVQ_CUDA_CHECK(cudaMemcpy(out4, static_cast<const char*>(workspace) + w.off_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  if (getenv("DVQ_TC_STATS_PRINT")) {
+    unsigned long long st[14];
+    DVQ_CUDA_CHECK(cudaMemcpy(st, static_cast<const char*>(workspace) + w.off_counters + 32, sizeof(st), cudaMemcpyDeviceToHost));
+    static const char* names[14] = {"producer.wait_stage_empty", "mma.wait_a_full", "mma.wait_acc_empty", "mma.total",
+                                    "conv.wait_stage_full", "conv.wait_a_empty", "conv.total", "epi0.wait_acc_full",
+                                    "epi4.wait_fin_empty", "epi0.wait_fin_full", "epi0.wait_sidx_empty", "epi0.total",
+                                    "gather.wait_sidx_full", "gather.total"};
+    for (int i = 0; i < 14; ++i) fprintf(stderr, "[dvq tc stats] %-28s %14llu cycles (sum over CTAs)\n", names[i], st[i]);
+  }
   return DVQ_OK;
 }
 

@@ -72,6 +72,7 @@ struct TcParams {
   int* counters;   // [0] refine-list length, [1] protocol error code
   int* row_list;
   uint32_t index_mask;  // 0xffffffe0 (kept in a register so key packing is one LOP3)
+  unsigned long long* stats;   // optional wait-time accounting (DVQ_TC_STATS builds)
   int64_t ntiles;
 };
 
@@ -130,7 +131,7 @@ __global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, CbMeta* 
     c.eh_norm_bound = 2.f * c.s_E * emax * (1.f + 1.f / 512.f);
     c.delta_max = 0.f;
     *cb = c;
-    counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0;
+    for (int i = 0; i < 64; ++i) counters[i] = 0;
   }
 }
 
@@ -196,7 +197,7 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
                : "memory");
 }
 // whole-warp wait: lane 0 spins (bounded), then every lane performs its own (now immediate) acquire
-__device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volatile int* errw, int code) {
+__device__ __noinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volatile int* errw, int code) {
   int ok = 1;
   if ((threadIdx.x & 31) == 0) ok = tc::mbar_wait(bar, parity, errw, code) ? 1 : 0;
   ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -210,6 +211,24 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {   // one arrival pe
   __syncwarp();
   if ((threadIdx.x & 31) == 0) tc::mbar_arrive(bar);
 }
+
+// Optional wait-time accounting (build with DVQ_TC_STATS=1): cycles spent in each wait site,
+// summed over the lanes that wait, flushed to stats[site] at the end of the kernel.
+#ifdef DVQ_TC_STATS
+#define STAT_DECL(n) long long stat_acc[n] = {}
+#define STAT_T0() const long long _t0 = clock64()
+#define STAT_ADD(i) stat_acc[i] += clock64() - _t0
+#define STAT_FLUSH(n, base)                                                              \
+  do {                                                                                   \
+    if ((threadIdx.x & 31) == 0)                                                         \
+      for (int _i = 0; _i < (n); ++_i) atomicAdd(p.stats + (base) + _i, (unsigned long long)stat_acc[_i]); \
+  } while (0)
+#else
+#define STAT_DECL(n)
+#define STAT_T0()
+#define STAT_ADD(i)
+#define STAT_FLUSH(n, base)
+#endif
 
 struct RowState {   // per (row, column-half) running result of the filter
   float m1;         // smallest key so far (index in the 5 low bits)
@@ -301,17 +320,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         const uint32_t n = min(16384u, L.bimg_bytes - off);
         tc::bulk_g2s(smem + L.bimg + off, p.bimg + off, n, &bar_b_full);
       }
+      STAT_DECL(1);
       for (int64_t it = 0; it < my_tiles; ++it) {
         const int64_t tile = blockIdx.x + it * gridDim.x;
         const int s = (int)(it & 1);
         const uint32_t ph = (uint32_t)((it >> 1) & 1);
-        if (!tc::mbar_wait(&bar_stage_empty[s], ph ^ 1u, errw, ERR_STAGE_EMPTY)) break;
+        { STAT_T0(); const bool w_ok = tc::mbar_wait(&bar_stage_empty[s], ph ^ 1u, errw, ERR_STAGE_EMPTY); STAT_ADD(0); if (!w_ok) break; }
         const int64_t row0 = tile * TM;
         const int rows = (int)min((int64_t)TM, p.N - row0);
         const uint32_t bytes = (uint32_t)rows * D * 4;
         tc::mbar_arrive_expect_tx(&bar_stage_full[s], bytes);
         tc::bulk_g2s(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
       }
+      STAT_FLUSH(1, 0);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -319,55 +340,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       bool ok = tc::mbar_wait(&bar_b_full, 0, errw, ERR_B_FULL);
       const uint32_t b_lbo = (uint32_t)K * 16, b_sbo = 128;
       const uint32_t a_lbo = A_CHUNK_BYTES, a_sbo = 128;
-      const uint32_t b_base = tc::smem_u32(smem + L.bimg);
+      // descriptors are (address >> 4) in the low bits: advancing by one k-step (two 8-wide k-chunks)
+      // is a constant add that never carries out of the 14-bit address field
+      const uint64_t a_step = (uint64_t)((2u * a_lbo) >> 4), b_step = (uint64_t)((2u * b_lbo) >> 4);
+      const uint64_t a_desc0[2] = {tc::make_smem_desc(tc::smem_u32(smem + L.a_img[0]), a_lbo, a_sbo),
+                                   tc::make_smem_desc(tc::smem_u32(smem + L.a_img[1]), a_lbo, a_sbo)};
+      const uint64_t b_desc0 = tc::make_smem_desc(tc::smem_u32(smem + L.bimg), b_lbo, b_sbo);
       uint32_t q = 0;
+      STAT_DECL(3);
+#ifdef DVQ_TC_STATS
+      const long long mma_t0 = clock64();
+#endif
       for (int64_t it = 0; ok && it < my_tiles; ++it) {
         const int a = (int)(it & 1);
-        if (!tc::mbar_wait(&bar_a_full[a], (uint32_t)((it >> 1) & 1), errw, ERR_A_FULL)) break;
+        { STAT_T0(); const bool w_ok = tc::mbar_wait(&bar_a_full[a], (uint32_t)((it >> 1) & 1), errw, ERR_A_FULL); STAT_ADD(0); if (!w_ok) break; }
         tc::tc_fence_after();
-        const uint32_t a_base = tc::smem_u32(smem + L.a_img[a]);
         for (int c = 0; c < nchunks; ++c, ++q) {
           const uint32_t t = q & 1u;
-          if (!tc::mbar_wait(&bar_acc_empty[t], ((q >> 1) & 1u) ^ 1u, errw, ERR_ACC_EMPTY)) { ok = false; break; }
+          { STAT_T0(); const bool w_ok = tc::mbar_wait(&bar_acc_empty[t], ((q >> 1) & 1u) ^ 1u, errw, ERR_ACC_EMPTY); STAT_ADD(1); if (!w_ok) { ok = false; break; } }
           tc::tc_fence_after();
           const int n = min(256, K - c * 256);
           const uint32_t idesc = tc::make_idesc_f16(128, n, 0);
           const uint32_t d_tmem = tmem_base + t * 256u;
-          const uint32_t bc = b_base + (uint32_t)c * 256u * 16u;
+          const uint64_t bc = b_desc0 + (uint64_t)((uint32_t)c * 256u);     // 256 codes * 16 B >> 4
+          uint64_t ad = a_desc0[a], bd = bc;
           uint32_t acc = 0;
+#pragma unroll 1
           for (int j = 0; j < nk; ++j) {   // zh . eh
-            tc::umma_f16(d_tmem, tc::make_smem_desc(a_base + (uint32_t)j * 2u * a_lbo, a_lbo, a_sbo),
-                         tc::make_smem_desc(bc + (uint32_t)j * 2u * b_lbo, b_lbo, b_sbo), idesc, acc);
-            acc = 1;
+            tc::umma_f16(d_tmem, ad, bd, idesc, acc);
+            acc = 1; ad += a_step; bd += b_step;
           }
-          for (int j = 0; j < nk; ++j)     // zl . eh
-            tc::umma_f16(d_tmem, tc::make_smem_desc(a_base + (uint32_t)(nk + j) * 2u * a_lbo, a_lbo, a_sbo),
-                         tc::make_smem_desc(bc + (uint32_t)j * 2u * b_lbo, b_lbo, b_sbo), idesc, 1);
-          tc::umma_f16(d_tmem, tc::make_smem_desc(a_base + (uint32_t)(2 * nk) * 2u * a_lbo, a_lbo, a_sbo),
-                       tc::make_smem_desc(bc + (uint32_t)nk * 2u * b_lbo, b_lbo, b_sbo), idesc, 1);   // fold
+          bd = bc;
+#pragma unroll 1
+          for (int j = 0; j < nk; ++j) {   // zl . eh
+            tc::umma_f16(d_tmem, ad, bd, idesc, 1);
+            ad += a_step; bd += b_step;
+          }
+          tc::umma_f16(d_tmem, ad, bd, idesc, 1);   // fold columns
           tc::umma_commit(&bar_acc_full[t]);
         }
         tc::umma_commit(&bar_a_empty[a]);
       }
+#ifdef DVQ_TC_STATS
+      stat_acc[2] = clock64() - mma_t0;
+#endif
+      STAT_FLUSH(3, 1);
     }
   } else if (warp < EPI_WARP0) {
     // ===================== converters: thread <-> tile row =====================
     const int r = (warp - CONV_WARP0) * 32 + lane;
     const CbMeta cb = *p.cb;
     const int nv = D / 4;   // float4 per row
+    STAT_DECL(3);
+#ifdef DVQ_TC_STATS
+    const long long conv_t0 = clock64();
+#endif
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int s = (int)(it & 1), a = (int)(it & 1);
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
       const int rows = (int)min((int64_t)TM, p.N - tile * TM);
-      if (!warp_wait(&bar_stage_full[s], ph, errw, ERR_STAGE_FULL)) break;
+      { STAT_T0(); const bool w_ok = warp_wait(&bar_stage_full[s], ph, errw, ERR_STAGE_FULL); STAT_ADD(0); if (!w_ok) break; }
       const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nv;
       // pass 1: squared norm (lane-rotated chunk order: conflict-free 128-bit reads)
       float nsq = 0.f;
       bool finite = true;
       if (r < rows) {
         for (int i = 0; i < nv; ++i) {
-          const int c4 = (i + lane) % nv;
+          const int c4 = (i + lane) & (nv - 1);
           const float4 v = src[c4];
           nsq = fmaf(v.x, v.x, nsq); nsq = fmaf(v.y, v.y, nsq); nsq = fmaf(v.z, v.z, nsq); nsq = fmaf(v.w, v.w, nsq);
         }
@@ -392,11 +432,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
                       + 16.f * fr * (1.f / 256.f);                             // ee rounding (r_n = fr / 256)
       float band = 2.f * eps * (1.f + 1.f / 16.f);
       if (degenerate) band = -1.f;    // marks "send to the exact kernel"
-      if (!warp_wait(&bar_a_empty[a], ph ^ 1u, errw, ERR_A_EMPTY)) break;
+      { STAT_T0(); const bool w_ok = warp_wait(&bar_a_empty[a], ph ^ 1u, errw, ERR_A_EMPTY); STAT_ADD(1); if (!w_ok) break; }
       // pass 2: convert and write the A image
       uint8_t* aimg = smem + L.a_img[a] + (r >> 3) * 128 + (r & 7) * 16;
       for (int i = 0; i < nv / 2; ++i) {
-        const int c8 = (i + lane) % (nv / 2);                           // 8-wide k-chunk
+        const int c8 = (i + lane) & (nv / 2 - 1);                       // 8-wide k-chunk
         const float4 v0 = src[2 * c8], v1 = src[2 * c8 + 1];
         const float x[8] = {v0.x * s_n, v0.y * s_n, v0.z * s_n, v0.w * s_n, v1.x * s_n, v1.y * s_n, v1.z * s_n, v1.w * s_n};
         __half2 hi[4], lo[4];
@@ -424,6 +464,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       tc::fence_proxy_async_smem();           // A image visible to the tensor core (async proxy)
       tc::mbar_arrive(&bar_a_full[a]);
     }
+#ifdef DVQ_TC_STATS
+    stat_acc[2] = clock64() - conv_t0;
+    if (warp != CONV_WARP0) { stat_acc[0] = stat_acc[1] = stat_acc[2] = 0; }
+#endif
+    STAT_FLUSH(3, 4);
   } else if (warp < GATHER_WARP0) {
     // ===================== epilogue: TMEM -> (min, ambiguity) per row =====================
     const int w = warp - EPI_WARP0;
@@ -433,6 +478,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t mask = p.index_mask;
     uint32_t q = 0;
+    STAT_DECL(5);
+#ifdef DVQ_TC_STATS
+    const long long epi_t0 = clock64();
+#endif
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t row0 = tile * TM;
@@ -445,33 +494,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       bool ok = true;
       for (int c = 0; c < nchunks; ++c, ++q) {
         const uint32_t t = q & 1u;
-        if (ok) ok = warp_wait(&bar_acc_full[t], (q >> 1) & 1u, errw, ERR_ACC_FULL);
+        if (ok) { STAT_T0(); ok = warp_wait(&bar_acc_full[t], (q >> 1) & 1u, errw, ERR_ACC_FULL); STAT_ADD(0); }
         if (!ok) continue;
         tc::tc_fence_after();
         if (c == 0) band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
         const int n = min(256, K - c * 256);
         const uint32_t tbase = tmem_base + lane_addr + t * 256u;
-        if (n == 256) {
-          // 4 sub-chunks per warp, software-pipelined: the next TMEM load is in flight while this one is reduced
-          uint32_t va[32], vb[32];
-          tc::tmem_ld32(tbase + (uint32_t)(half + 0) * 32u, va);
+        // my sub-chunks of this chunk: half, half+2, ...  Processed two per iteration from two register
+        // sets so the next TMEM load is always in flight while the current values are reduced; the
+        // loop is kept rolled (unroll 1) so the whole epilogue stays inside the instruction cache.
+        const int nsub = (n / 32 - half + 1) / 2;
+        uint32_t va[32], vb[32];
+        if (nsub > 0) tc::tmem_ld32(tbase + (uint32_t)half * 32u, va);
+#pragma unroll 1
+        for (int i = 0; i < nsub; i += 2) {
+          const int sc0 = half + 2 * i, sc1 = sc0 + 2;
           tmem_ld_wait_dep(va);
-          tc::tmem_ld32(tbase + (uint32_t)(half + 2) * 32u, vb);
-          filter_subchunk(va, mask, c * 256 + (half + 0) * 32, band, st);
-          tmem_ld_wait_dep(vb);
-          tc::tmem_ld32(tbase + (uint32_t)(half + 4) * 32u, va);
-          filter_subchunk(vb, mask, c * 256 + (half + 2) * 32, band, st);
-          tmem_ld_wait_dep(va);
-          tc::tmem_ld32(tbase + (uint32_t)(half + 6) * 32u, vb);
-          filter_subchunk(va, mask, c * 256 + (half + 4) * 32, band, st);
-          tmem_ld_wait_dep(vb);
-          filter_subchunk(vb, mask, c * 256 + (half + 6) * 32, band, st);
-        } else {
-          for (int sc = half; sc * 32 < n; sc += 2) {
-            uint32_t v[32];
-            tc::tmem_ld32(tbase + (uint32_t)sc * 32u, v);
-            tmem_ld_wait_dep(v);
-            filter_subchunk(v, mask, c * 256 + sc * 32, band, st);
+          if (i + 1 < nsub) tc::tmem_ld32(tbase + (uint32_t)sc1 * 32u, vb);
+          filter_subchunk(va, mask, c * 256 + sc0 * 32, band, st);
+          if (i + 1 < nsub) {
+            tmem_ld_wait_dep(vb);
+            if (i + 2 < nsub) tc::tmem_ld32(tbase + (uint32_t)(sc1 + 2) * 32u, va);
+            filter_subchunk(vb, mask, c * 256 + sc1 * 32, band, st);
           }
         }
         tc::tc_fence_before();
@@ -483,11 +527,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       float* fin_cnt = fin_key + 2 * TM;
       if (half == 1) {
         // hand this half's result to the half-0 warp that owns the same rows
-        if (!warp_wait(&bar_fin_empty[slot], sph ^ 1u, errw, ERR_FIN)) break;
+        { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_empty[slot], sph ^ 1u, errw, ERR_FIN); STAT_ADD(1); if (!w_ok) break; }
         fin_key[r] = st.m1; fin_col[r] = st.col; fin_cnt[r] = st.cnt;
         warp_arrive(&bar_fin_full[slot]);
       } else {
-        if (!warp_wait(&bar_fin_full[slot], sph, errw, ERR_FIN)) break;
+        { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_full[slot], sph, errw, ERR_FIN); STAT_ADD(2); if (!w_ok) break; }
         const float ko = fin_key[r];
         const int co = fin_col[r];
         const float no = fin_cnt[r];
@@ -498,7 +542,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         else            { col = st.col; flag = (st.cnt > 0.5f) || (ko - st.m1 <= band); }
         if (band < 0.f) flag = true;
         flag = flag && (r < rows);
-        if (!warp_wait(&bar_sidx_empty[slot], sph ^ 1u, errw, ERR_SIDX)) break;
+        { STAT_T0(); const bool w_ok = warp_wait(&bar_sidx_empty[slot], sph ^ 1u, errw, ERR_SIDX); STAT_ADD(3); if (!w_ok) break; }
         reinterpret_cast<int*>(smem + L.sidx)[slot * TM + r] = flag ? -1 : col;
         warp_arrive(&bar_sidx_full[slot]);
         // undecided rows -> list for the exact FP32 kernel (one atomic per warp that has any)
@@ -511,46 +555,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         }
       }
     }
+#ifdef DVQ_TC_STATS
+    stat_acc[4] = clock64() - epi_t0;
+    if (w != 0 && w != 4) { for (int i = 0; i < 5; ++i) stat_acc[i] = 0; }
+    if (w == 4) { stat_acc[0] = 0; stat_acc[4] = 0; }
+#endif
+    STAT_FLUSH(5, 7);
   } else {
     // ===================== gather: z_q, idx, SSE, histogram for the decided rows =====================
     const int gw = warp - GATHER_WARP0;
     int* shist = reinterpret_cast<int*>(smem + L.hist);
-    const int nv = D / 4;                              // float4 slots per row
+    const int nv = D / 4;                              // float4 slots per row (power of two)
     const int rows_per_warp = TM / GATHER_WARPS;
-    const int slots = rows_per_warp * nv;              // float4 slots this warp owns per tile
+    // lane -> (row, float4 column) without divisions: a row is covered by lpr = min(nv, 32) lanes in
+    // `parts` = nv / lpr passes; one warp-step covers 32 / lpr rows (or one part of one row).
+    const int lpr = nv < 32 ? nv : 32;
+    const int lpr_shift = 31 - __clz(lpr);
+    const int parts_shift = 31 - __clz(nv / lpr);
+    const int rows_per_step_shift = 5 - lpr_shift;     // log2(32 / lpr)
+    const int steps = (rows_per_warp << parts_shift) >> rows_per_step_shift;
+    const int c4_lane = lane & (lpr - 1), rsub = lane >> lpr_shift;
     double sse_acc = 0.0;
     constexpr int U = 8;                               // loads in flight per lane (x2 in train mode)
+    STAT_DECL(2);
+#ifdef DVQ_TC_STATS
+    const long long g_t0 = clock64();
+#endif
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t row0 = tile * TM;
       const int rows = (int)min((int64_t)TM, p.N - row0);
       const int slot = (int)(it & 1);
       const uint32_t sph = (uint32_t)((it >> 1) & 1);
-      if (!warp_wait(&bar_sidx_full[slot], sph, errw, ERR_SIDX)) break;
+      { STAT_T0(); const bool w_ok = warp_wait(&bar_sidx_full[slot], sph, errw, ERR_SIDX); STAT_ADD(0); if (!w_ok) break; }
       const int* sidx = reinterpret_cast<const int*>(smem + L.sidx) + slot * TM;
+      const float* zt = p.z + row0 * D;
+      float* ot = p.zq + row0 * D;
       float lsse = 0.f;
-      for (int base = 0; base < slots; base += U * 32) {
+#pragma unroll 1
+      for (int t0 = 0; t0 < steps; t0 += U) {
         float4 e4[U], z4[U];
         int kk[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int sl = base + u * 32 + lane;
-          const int rr = gw * rows_per_warp + sl / nv;
-          const int c4 = sl - (sl / nv) * nv;
+          const int t = t0 + u;
+          const int rr = gw * rows_per_warp + (((t >> parts_shift) << rows_per_step_shift) | rsub);
+          const int c4 = ((t & ((1 << parts_shift) - 1)) << 5) | c4_lane;
           int k = -1;
-          if (sl < slots && rr < rows) k = sidx[rr];
+          if (t < steps && rr < rows) k = sidx[rr];
           kk[u] = k;
           if (k >= 0) {
             e4[u] = ldg4(p.E + (int64_t)k * D + c4 * 4);
-            if (p.train) z4[u] = ldg4(p.z + (row0 + rr) * D + c4 * 4);
+            if (p.train) z4[u] = ldg4(zt + rr * D + c4 * 4);
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (kk[u] < 0) continue;
-          const int sl = base + u * 32 + lane;
-          const int rr = gw * rows_per_warp + sl / nv;
-          const int c4 = sl - (sl / nv) * nv;
+          const int t = t0 + u;
+          const int rr = gw * rows_per_warp + (((t >> parts_shift) << rows_per_step_shift) | rsub);
+          const int c4 = ((t & ((1 << parts_shift) - 1)) << 5) | c4_lane;
           float4 o4 = e4[u];
           if (p.train) {
             const float dx = __fsub_rn(e4[u].x, z4[u].x), dy = __fsub_rn(e4[u].y, z4[u].y);
@@ -558,7 +622,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
             lsse = fmaf(dx, dx, lsse); lsse = fmaf(dy, dy, lsse); lsse = fmaf(dz, dz, lsse); lsse = fmaf(dw, dw, lsse);
             o4 = make_float4(__fadd_rn(z4[u].x, dx), __fadd_rn(z4[u].y, dy), __fadd_rn(z4[u].z, dz), __fadd_rn(z4[u].w, dw));
           }
-          *reinterpret_cast<float4*>(p.zq + (row0 + rr) * D + c4 * 4) = o4;
+          *reinterpret_cast<float4*>(ot + rr * D + c4 * 4) = o4;
           if (c4 == 0) {
             p.idx[row0 + rr] = (int64_t)kk[u];
             if (p.train) atomicAdd(&shist[kk[u]], 1);
@@ -568,6 +632,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       warp_arrive(&bar_sidx_empty[slot]);
       sse_acc += (double)lsse;
     }
+#ifdef DVQ_TC_STATS
+    stat_acc[1] = clock64() - g_t0;
+    if (gw != 0) { stat_acc[0] = stat_acc[1] = 0; }
+#endif
+    STAT_FLUSH(2, 12);
     // ---- CTA totals (only the gather warps touch shist after the start-up clear) ----
     if (p.train) {
       asm volatile("bar.sync 1, %0;" ::"r"(GATHER_WARPS * 32) : "memory");
@@ -590,7 +659,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 
 bool vq_tc_supported(int64_t N, int K, int D) {
   if (N <= 0 || N > 2147483647LL - 256) return false;
-  if (D % 16 != 0 || D < 16 || D > 256) return false;
+  if (D < 16 || D > 256 || (D & (D - 1)) != 0) return false;   // power of two: index math is masks/shifts
   if (K % 32 != 0 || K < 32 || K > 4096) return false;
   return smem_layout(K, D).total + 128 + 512 <= 227 * 1024;   // + alignment slack + static barriers
 }
@@ -621,6 +690,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.N = N; p.K = K; p.D = D; p.train = train;
   p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list;
   p.index_mask = 0xffffffe0u;
+  p.stats = reinterpret_cast<unsigned long long*>(counters + 8);
   p.ntiles = (N + TM - 1) / TM;
   const size_t smem = L.total + 128;
   DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
