@@ -20,12 +20,13 @@
 // minimum; the count of such keys is kept with a running (never too small) threshold, exact
 // resets, and FFMA.SAT arithmetic on the FMA pipe.  Undecided rows (a few %) go to the list.
 //
-// Pipeline (one persistent CTA per SM, 16 warps):
+// Pipeline (one persistent CTA per SM, 18 warps; every SM sub-partition hosts 1 converter, 2 epilogue
+// and 1 gather warp — a lone warp issues only ~1 instruction per 5 cycles, so work is spread wide):
 //   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B)
 //   warp 1      MMA      : single elected thread issues tcgen05.mma, commits to mbarriers
 //   warps 2-5   convert  : staging -> registers -> scales / norms / bounds -> FP16 A image (2 stages)
 //   warps 6-13  epilogue : tcgen05.ld TMEM (software-pipelined) -> keys -> argmin + ambiguity count
-//   warps 14-15 gather   : E[idx] (128-bit, 8-16 loads in flight per lane), z_q, SSE, smem histogram, idx
+//   warps 14-17 gather   : E[idx] (128-bit, 8-16 loads in flight per lane), z_q, SSE, smem histogram, idx
 // TMEM: 512 columns = 2 accumulator stages of 256, so the MMA of one 256-code chunk overlaps the
 // epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays resident in
 // shared memory for the life of the CTA.
@@ -42,7 +43,7 @@ constexpr int A_CHUNK_BYTES = TM * 16 + 32;  // one 8-wide k-chunk of the A imag
 constexpr int CONV_WARP0 = 2;
 constexpr int EPI_WARP0 = 6;
 constexpr int GATHER_WARP0 = 14;
-constexpr int GATHER_WARPS = 2;
+constexpr int GATHER_WARPS = 4;
 constexpr int NUM_WARPS = GATHER_WARP0 + GATHER_WARPS;
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int META_SLOTS = 4;
@@ -330,7 +331,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         const int rows = (int)min((int64_t)TM, p.N - row0);
         const uint32_t bytes = (uint32_t)rows * D * 4;
         tc::mbar_arrive_expect_tx(&bar_stage_full[s], bytes);
-        tc::bulk_g2s(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
+        if (p.train) tc::bulk_g2s_keep(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
+        else tc::bulk_g2s(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
       }
       STAT_FLUSH(1, 0);
     }
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           const uint32_t idesc = tc::make_idesc_f16(128, n, 0);
           const uint32_t d_tmem = tmem_base + t * 256u;
           const uint64_t bc = b_desc0 + (uint64_t)((uint32_t)c * 256u);     // 256 codes * 16 B >> 4
-          uint64_t ad = a_desc0[a], bd = bc;
+          uint64_t ad = a ? a_desc0[1] : a_desc0[0], bd = bc;
           uint32_t acc = 0;
 #pragma unroll 1
           for (int j = 0; j < nk; ++j) {   // zh . eh
@@ -500,23 +502,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         if (c == 0) band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
         const int n = min(256, K - c * 256);
         const uint32_t tbase = tmem_base + lane_addr + t * 256u;
-        // my sub-chunks of this chunk: half, half+2, ...  Processed two per iteration from two register
-        // sets so the next TMEM load is always in flight while the current values are reduced; the
-        // loop is kept rolled (unroll 1) so the whole epilogue stays inside the instruction cache.
-        const int nsub = (n / 32 - half + 1) / 2;
-        uint32_t va[32], vb[32];
-        if (nsub > 0) tc::tmem_ld32(tbase + (uint32_t)half * 32u, va);
+        // my sub-chunks of this chunk: half, half+2, ...  The loop is kept rolled so the epilogue stays
+        // inside the instruction cache; the TMEM load latency is covered by the other warps of the
+        // sub-partition (register budget: 18 warps x 96).
 #pragma unroll 1
-        for (int i = 0; i < nsub; i += 2) {
-          const int sc0 = half + 2 * i, sc1 = sc0 + 2;
-          tmem_ld_wait_dep(va);
-          if (i + 1 < nsub) tc::tmem_ld32(tbase + (uint32_t)sc1 * 32u, vb);
-          filter_subchunk(va, mask, c * 256 + sc0 * 32, band, st);
-          if (i + 1 < nsub) {
-            tmem_ld_wait_dep(vb);
-            if (i + 2 < nsub) tc::tmem_ld32(tbase + (uint32_t)(sc1 + 2) * 32u, va);
-            filter_subchunk(vb, mask, c * 256 + sc1 * 32, band, st);
-          }
+        for (int sc = half; sc * 32 < n; sc += 2) {
+          uint32_t v[32];
+          tc::tmem_ld32(tbase + (uint32_t)sc * 32u, v);
+          tmem_ld_wait_dep(v);
+          filter_subchunk(v, mask, c * 256 + sc * 32, band, st);
         }
         tc::tc_fence_before();
         warp_arrive(&bar_acc_empty[t]);
@@ -576,7 +570,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     const int steps = (rows_per_warp << parts_shift) >> rows_per_step_shift;
     const int c4_lane = lane & (lpr - 1), rsub = lane >> lpr_shift;
     double sse_acc = 0.0;
-    constexpr int U = 8;                               // loads in flight per lane (x2 in train mode)
+    constexpr int U = 4;                               // row-steps in flight per lane (x2 loads in train mode)
     STAT_DECL(2);
 #ifdef DVQ_TC_STATS
     const long long g_t0 = clock64();
@@ -606,7 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           kk[u] = k;
           if (k >= 0) {
             e4[u] = ldg4(p.E + (int64_t)k * D + c4 * 4);
-            if (p.train) z4[u] = ldg4(zt + rr * D + c4 * 4);
+            if (p.train) z4[u] = __ldcs(reinterpret_cast<const float4*>(zt + rr * D + c4 * 4));   // last use of this tile
           }
         }
 #pragma unroll
@@ -622,7 +616,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
             lsse = fmaf(dx, dx, lsse); lsse = fmaf(dy, dy, lsse); lsse = fmaf(dz, dz, lsse); lsse = fmaf(dw, dw, lsse);
             o4 = make_float4(__fadd_rn(z4[u].x, dx), __fadd_rn(z4[u].y, dy), __fadd_rn(z4[u].z, dz), __fadd_rn(z4[u].w, dw));
           }
-          *reinterpret_cast<float4*>(ot + rr * D + c4 * 4) = o4;
+          __stcs(reinterpret_cast<float4*>(ot + rr * D + c4 * 4), o4);   // streaming: never re-read
           if (c4 == 0) {
             p.idx[row0 + rr] = (int64_t)kk[u];
             if (p.train) atomicAdd(&shist[kk[u]], 1);
