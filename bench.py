@@ -54,7 +54,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled every 100 ms while the benchmark runs; the median SM
+    clock is taken over the samples drawn under load (power above idle)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -66,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -86,8 +87,17 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
+        pw = []
         for r in self.rows:
             try:
+                pw.append(float(r[3]))
+            except Exception:
+                pass
+        load_floor = (min(pw) + 0.25 * (max(pw) - min(pw))) if pw else 0.0
+        for r in self.rows:
+            try:
+                if float(r[3]) < load_floor:
+                    continue
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
                 continue
@@ -212,14 +222,16 @@ def main():
             tdist.barrier()
             torch.cuda.synchronize(dev)
 
+    # clocks / throttle reasons are sampled from the first warm-up step to the end of the e2e leg (the
+    # device-resident timed region alone can be shorter than one 100 ms sampling period)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         out = step()
     fence()
 
     # ---- timed region: device-resident inputs --------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     _cabi.lib.dvq_profile_enable(1)
     launches0 = _cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -234,7 +246,6 @@ def main():
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = _cabi.launch_count() - launches0
     _cabi.lib.dvq_profile_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
@@ -265,6 +276,7 @@ def main():
     e2e_value = N_PER_GPU * world * e2e_steps / e2e_s
     same_idx = bool(torch.equal(idx_host, idx.cpu()))
     hq.close()
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         hbm_gbs, bf16_tf, peak_src = measured_peaks()
