@@ -20,13 +20,13 @@
 // minimum; the count of such keys is kept with a running (never too small) threshold, exact
 // resets, and FFMA.SAT arithmetic on the FMA pipe.  Undecided rows (a few %) go to the list.
 //
-// Pipeline (one persistent CTA per SM, 18 warps; every SM sub-partition hosts 1 converter, 2 epilogue
+// Pipeline (one persistent CTA per SM, 22 warps; every SM sub-partition hosts 1 converter, 3 epilogue
 // and 1 gather warp — a lone warp issues only ~1 instruction per 5 cycles, so work is spread wide):
 //   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B)
 //   warp 1      MMA      : single elected thread issues tcgen05.mma, commits to mbarriers
 //   warps 2-5   convert  : staging -> registers -> scales / norms / bounds -> FP16 A image (2 stages)
-//   warps 6-13  epilogue : tcgen05.ld TMEM (software-pipelined) -> keys -> argmin + ambiguity count
-//   warps 14-17 gather   : E[idx] (128-bit, 8-16 loads in flight per lane), z_q, SSE, smem histogram, idx
+//   warps 6-17  epilogue : tcgen05.ld TMEM (software-pipelined) -> keys -> argmin + ambiguity count
+//   warps 18-21 gather   : E[idx] (128-bit, 8-16 loads in flight per lane), z_q, SSE, smem histogram, idx
 // TMEM: 512 columns = 2 accumulator stages of 256, so the MMA of one 256-code chunk overlaps the
 // epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays resident in
 // shared memory for the life of the CTA.
@@ -42,7 +42,9 @@ constexpr int TM = 128;                 // rows per tile
 constexpr int A_CHUNK_BYTES = TM * 16 + 32;  // one 8-wide k-chunk of the A image (+32 B: bank spreading)
 constexpr int CONV_WARP0 = 2;
 constexpr int EPI_WARP0 = 6;
-constexpr int GATHER_WARP0 = 14;
+constexpr int EPQ = 3;                       // epilogue warps per TMEM lane quarter (they split the columns)
+constexpr int EPI_WARPS = 4 * EPQ;
+constexpr int GATHER_WARP0 = EPI_WARP0 + EPI_WARPS;
 constexpr int GATHER_WARPS = 4;
 constexpr int NUM_WARPS = GATHER_WARP0 + GATHER_WARPS;
 constexpr int NTHREADS = NUM_WARPS * 32;
@@ -95,7 +97,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   L.stage[0] = off; off += L.stage_bytes;
   L.stage[1] = off; off += L.stage_bytes;
   L.meta = off; off += META_SLOTS * TM * 4;
-  L.fin = off; off += 2 * TM * 12;      // 2 slots of (key, col, cnt) from the half-1 warps
+  L.fin = off; off += (EPQ - 1) * TM * 12;   // (EPQ-1) helper warps x (key, col, cnt); single slot
   L.sidx = off; off += 2 * TM * 4;      // 2 slots of final code index (-1: undecided)
   L.hist = off; off += (uint32_t)K * 4;
   L.total = off;
@@ -197,16 +199,17 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
                :
                : "memory");
 }
-// whole-warp wait: lane 0 spins (bounded), then every lane performs its own (now immediate) acquire
-__device__ __noinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volatile int* errw, int code) {
-  int ok = 1;
-  if ((threadIdx.x & 31) == 0) ok = tc::mbar_wait(bar, parity, errw, code) ? 1 : 0;
-  ok = __shfl_sync(0xffffffffu, ok, 0);
-  if (ok) {
-    for (int i = 0; i < 1024 && !tc::mbar_try_wait(bar, parity); ++i) {}
+// whole-warp wait: every lane sleeps on the barrier (try_wait with a suspend hint wakes on completion);
+// bounded, so a protocol bug sets the error word instead of hanging the GPU
+__device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volatile int* errw, int code) {
+  uint32_t spins = 0;
+  while (!tc::mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 16) || *errw != 0) {
+      if (*errw == 0) *errw = code;
+      break;
+    }
   }
-  __syncwarp();
-  return ok != 0;
+  return *errw == 0;
 }
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {   // one arrival per warp, after all lanes are done
   __syncwarp();
@@ -230,6 +233,13 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {   // one arrival pe
 #define STAT_ADD(i)
 #define STAT_FLUSH(n, base)
 #endif
+
+// float(h) - a in one FHADD (PTX mixed-precision sub, sm_100+): h is one half of a packed pair
+__device__ __forceinline__ float half_minus_float(uint32_t h16, float a) {
+  float r;
+  asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(r) : "h"((unsigned short)h16), "f"(a));
+  return r;
+}
 
 struct RowState {   // per (row, column-half) running result of the filter
   float m1;         // smallest key so far (index in the 5 low bits)
@@ -271,6 +281,9 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], uint32_t mask
   st.cnt += (c0 + c1) + (c2 + c3);
 }
 
+// DT > 0: e_dim known at compile time (strides, trip counts and index masks become immediates and the
+// role loops unroll); DT == 0: generic.  TRAIN selects the straight-through / SSE / histogram epilogue.
+template <int DT, bool TRAIN>
 __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_stage_full[2], bar_stage_empty[2], bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2], bar_b_full;
@@ -278,9 +291,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   __shared__ uint32_t tmem_slot;
   __shared__ int serr;
 
-  const SmemLayout L = smem_layout(p.K, p.D);
+  const int D = DT > 0 ? DT : p.D;
+  const int K = p.K;
+  const SmemLayout L = smem_layout(K, D);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int D = p.D, K = p.K;
   const int nk = D / 16;                       // k-steps per product
   const int nchunks = (K + 255) / 256;         // accumulator chunks per tile
   const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
@@ -293,8 +307,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       tc::mbar_init(&bar_a_full[i], 128);       // every converter thread (after its own proxy fence)
       tc::mbar_init(&bar_a_empty[i], 1);
       tc::mbar_init(&bar_acc_full[i], 1);
-      tc::mbar_init(&bar_acc_empty[i], 8);      // one arrival per epilogue warp
-      tc::mbar_init(&bar_fin_full[i], 4);       // half-1 epilogue warps -> half-0
+      tc::mbar_init(&bar_acc_empty[i], EPI_WARPS);   // one arrival per epilogue warp
+      tc::mbar_init(&bar_fin_full[i], 4 * (EPQ - 1));   // helper epilogue warps -> the owner warp of the rows
       tc::mbar_init(&bar_fin_empty[i], 4);
       tc::mbar_init(&bar_sidx_full[i], 4);      // half-0 epilogue warps -> gather warps
       tc::mbar_init(&bar_sidx_empty[i], GATHER_WARPS);
@@ -331,7 +345,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         const int rows = (int)min((int64_t)TM, p.N - row0);
         const uint32_t bytes = (uint32_t)rows * D * 4;
         tc::mbar_arrive_expect_tx(&bar_stage_full[s], bytes);
-        if (p.train) tc::bulk_g2s_keep(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
+        if (TRAIN) tc::bulk_g2s_keep(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
         else tc::bulk_g2s(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
       }
       STAT_FLUSH(1, 0);
@@ -374,8 +388,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           }
           bd = bc;
 #pragma unroll 1
-          for (int j = 0; j < nk; ++j) {   // zl . eh
-            tc::umma_f16(d_tmem, ad, bd, idesc, 1);
+          for (int j = 0; j < nk; ++j) {   // zl . eh  (A holds -zl: negate-A bit 13 of the descriptor)
+            tc::umma_f16(d_tmem, ad, bd, idesc | (1u << 13), 1);
             ad += a_step; bd += b_step;
           }
           tc::umma_f16(d_tmem, ad, bd, idesc, 1);   // fold columns
@@ -441,12 +455,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         const int c8 = (i + lane) & (nv / 2 - 1);                       // 8-wide k-chunk
         const float4 v0 = src[2 * c8], v1 = src[2 * c8 + 1];
         const float x[8] = {v0.x * s_n, v0.y * s_n, v0.z * s_n, v0.w * s_n, v1.x * s_n, v1.y * s_n, v1.z * s_n, v1.w * s_n};
+        // hi = fp16(x); the second term is stored NEGATED, nl = fp16(hi - x) (one FHADD each, no unpack); the
+        // MMA issuer sets the A-negate bit of the instruction descriptor for the zl.eh products
         __half2 hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           hi[e] = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
-          const float2 hf = __half22float2(hi[e]);
-          lo[e] = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+          const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi[e]);
+          lo[e] = __floats2half2_rn(half_minus_float(hb & 0xffffu, x[2 * e]), half_minus_float(hb >> 16, x[2 * e + 1]));
         }
         *reinterpret_cast<uint4*>(aimg + (size_t)c8 * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(hi);
         *reinterpret_cast<uint4*>(aimg + (size_t)(nv / 2 + c8) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(lo);
@@ -475,7 +491,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     // ===================== epilogue: TMEM -> (min, ambiguity) per row =====================
     const int w = warp - EPI_WARP0;
     const int quarter = warp & 3;       // TMEM lanes this warp may access: 32*(warp_id % 4)
-    const int half = w >> 2;            // which sub-chunks of each accumulator chunk
+    const int wq = w >> 2;              // 0 = owner of these rows, 1..EPQ-1 = helpers (they split the columns)
     const int r = quarter * 32 + lane;  // tile row == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t mask = p.index_mask;
@@ -502,11 +518,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         if (c == 0) band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
         const int n = min(256, K - c * 256);
         const uint32_t tbase = tmem_base + lane_addr + t * 256u;
-        // my sub-chunks of this chunk: half, half+2, ...  The loop is kept rolled so the epilogue stays
-        // inside the instruction cache; the TMEM load latency is covered by the other warps of the
-        // sub-partition (register budget: 18 warps x 96).
+        // my sub-chunks of this chunk: every EPQ-th one; the owner warp (wq == 0) takes the residue class
+        // with the fewest members (it also merges, writes idx and the histogram).  The loop is kept rolled so the epilogue
+        // stays inside the instruction cache; the TMEM load latency is covered by the other warps of
+        // the sub-partition.
 #pragma unroll 1
-        for (int sc = half; sc * 32 < n; sc += 2) {
+        for (int sc = (wq + EPQ - 1) % EPQ; sc * 32 < n; sc += EPQ) {
           uint32_t v[32];
           tc::tmem_ld32(tbase + (uint32_t)sc * 32u, v);
           tmem_ld_wait_dep(v);
@@ -516,29 +533,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         warp_arrive(&bar_acc_empty[t]);
       }
       if (*errw) break;
-      float* fin_key = reinterpret_cast<float*>(smem + L.fin) + slot * 3 * TM;
-      int* fin_col = reinterpret_cast<int*>(fin_key + TM);
-      float* fin_cnt = fin_key + 2 * TM;
-      if (half == 1) {
-        // hand this half's result to the half-0 warp that owns the same rows
-        { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_empty[slot], sph ^ 1u, errw, ERR_FIN); STAT_ADD(1); if (!w_ok) break; }
-        fin_key[r] = st.m1; fin_col[r] = st.col; fin_cnt[r] = st.cnt;
-        warp_arrive(&bar_fin_full[slot]);
+      float* fin_base = reinterpret_cast<float*>(smem + L.fin);   // single slot: phase flips every tile
+      const uint32_t fph = (uint32_t)(it & 1);
+      if (wq > 0) {
+        // hand this warp's partial result to the owner warp of the same rows
+        float* fin_key = fin_base + (wq - 1) * 3 * TM;
+        { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_empty[0], fph ^ 1u, errw, ERR_FIN); STAT_ADD(1); if (!w_ok) break; }
+        fin_key[r] = st.m1;
+        reinterpret_cast<int*>(fin_key + TM)[r] = st.col;
+        fin_key[2 * TM + r] = st.cnt;
+        warp_arrive(&bar_fin_full[0]);
       } else {
-        { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_full[slot], sph, errw, ERR_FIN); STAT_ADD(2); if (!w_ok) break; }
-        const float ko = fin_key[r];
-        const int co = fin_col[r];
-        const float no = fin_cnt[r];
-        warp_arrive(&bar_fin_empty[slot]);
-        bool flag;
-        int col;
-        if (ko < st.m1) { col = co; flag = (no > 0.5f) || (st.m1 - ko <= band); }
-        else            { col = st.col; flag = (st.cnt > 0.5f) || (ko - st.m1 <= band); }
+        { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_full[0], fph, errw, ERR_FIN); STAT_ADD(2); if (!w_ok) break; }
+        // merge the helpers' states: keep the smaller minimum; the loser's minimum either falls inside
+        // the winner's band (ambiguous) or voids the loser's count entirely
+        float m1 = st.m1, cnt = st.cnt;
+        int col = st.col;
+        bool flag = false;
+#pragma unroll
+        for (int h = 0; h < EPQ - 1; ++h) {
+          const float* fin_key = fin_base + h * 3 * TM;
+          const float ko = fin_key[r];
+          const int co = reinterpret_cast<const int*>(fin_key + TM)[r];
+          const float no = fin_key[2 * TM + r];
+          if (ko < m1) { flag = (m1 - ko <= band); m1 = ko; col = co; cnt = no; }
+          else         { flag = flag || (ko - m1 <= band); }
+        }
+        warp_arrive(&bar_fin_empty[0]);
+        flag = flag || (cnt > 0.5f);
         if (band < 0.f) flag = true;
-        flag = flag && (r < rows);
+        const bool valid = r < rows;
+        flag = flag && valid;
         { STAT_T0(); const bool w_ok = warp_wait(&bar_sidx_empty[slot], sph ^ 1u, errw, ERR_SIDX); STAT_ADD(3); if (!w_ok) break; }
-        reinterpret_cast<int*>(smem + L.sidx)[slot * TM + r] = flag ? -1 : col;
+        // code for the gather warps: sign bit = "undecided" (its z_q row is rewritten by the exact kernel,
+        // its SSE / histogram contribution is left to it)
+        reinterpret_cast<int*>(smem + L.sidx)[slot * TM + r] = (col * D * 4) | (flag ? 0x80000000 : 0);   // byte offset into E
         warp_arrive(&bar_sidx_full[slot]);
+        if (valid && !flag) {
+          p.idx[row0 + r] = (int64_t)col;          // 32 lanes x 8 B: one coalesced 256-byte store per warp
+          if (TRAIN) atomicAdd(reinterpret_cast<int*>(smem + L.hist) + col, 1);
+        }
         // undecided rows -> list for the exact FP32 kernel (one atomic per warp that has any)
         const unsigned bal = __ballot_sync(0xffffffffu, flag);
         if (bal) {
@@ -552,7 +586,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 #ifdef DVQ_TC_STATS
     stat_acc[4] = clock64() - epi_t0;
     if (w != 0 && w != 4) { for (int i = 0; i < 5; ++i) stat_acc[i] = 0; }
-    if (w == 4) { stat_acc[0] = 0; stat_acc[4] = 0; }
+    if (w == 4) { stat_acc[0] = 0; stat_acc[4] = 0; }   // w == 4: first helper warp
 #endif
     STAT_FLUSH(5, 7);
   } else {
@@ -561,16 +595,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     int* shist = reinterpret_cast<int*>(smem + L.hist);
     const int nv = D / 4;                              // float4 slots per row (power of two)
     const int rows_per_warp = TM / GATHER_WARPS;
-    // lane -> (row, float4 column) without divisions: a row is covered by lpr = min(nv, 32) lanes in
-    // `parts` = nv / lpr passes; one warp-step covers 32 / lpr rows (or one part of one row).
+    // lane -> (row, float4 column): a row is covered by lpr = min(nv, 32) lanes in `parts` = nv / lpr
+    // passes; one warp-step covers rps = 32 / lpr rows.  All index math is shifts / loop-invariant
+    // pointer bumps (immediates when e_dim is a template constant).
     const int lpr = nv < 32 ? nv : 32;
     const int lpr_shift = 31 - __clz(lpr);
-    const int parts_shift = 31 - __clz(nv / lpr);
-    const int rows_per_step_shift = 5 - lpr_shift;     // log2(32 / lpr)
-    const int steps = (rows_per_warp << parts_shift) >> rows_per_step_shift;
+    const int parts = nv / lpr;
+    const int rps = 32 >> lpr_shift;
     const int c4_lane = lane & (lpr - 1), rsub = lane >> lpr_shift;
+    const int nsteps = rows_per_warp / rps;            // row-steps per warp per tile (per part)
+    const int rbase = gw * rows_per_warp + rsub;
     double sse_acc = 0.0;
-    constexpr int U = 4;                               // row-steps in flight per lane (x2 loads in train mode)
+    constexpr int U = 8;                               // row-steps in flight per lane (x2 loads in train mode)
     STAT_DECL(2);
 #ifdef DVQ_TC_STATS
     const long long g_t0 = clock64();
@@ -582,44 +618,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int slot = (int)(it & 1);
       const uint32_t sph = (uint32_t)((it >> 1) & 1);
       { STAT_T0(); const bool w_ok = warp_wait(&bar_sidx_full[slot], sph, errw, ERR_SIDX); STAT_ADD(0); if (!w_ok) break; }
-      const int* sidx = reinterpret_cast<const int*>(smem + L.sidx) + slot * TM;
-      const float* zt = p.z + row0 * D;
-      float* ot = p.zq + row0 * D;
+      const int* sp = reinterpret_cast<const int*>(smem + L.sidx) + slot * TM + rbase;
       float lsse = 0.f;
+      const bool full_tile = rows == TM;
 #pragma unroll 1
-      for (int t0 = 0; t0 < steps; t0 += U) {
-        float4 e4[U], z4[U];
-        int kk[U];
+      for (int part = 0; part < parts; ++part) {
+        const int c4 = (part << 5) | c4_lane;
+        const char* ec = reinterpret_cast<const char*>(p.E + c4 * 4);
+        const float* zp = p.z + (row0 + rbase) * D + c4 * 4;
+        float* op = p.zq + (row0 + rbase) * D + c4 * 4;
+        if (full_tile && (nsteps % U) == 0) {
+          // fast path: no per-row checks, loads of a whole batch issued before any is consumed
+#pragma unroll 1
+          for (int t0 = 0; t0 < nsteps; t0 += U) {
+            float4 e4[U], z4[U];
+            int kk[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int t = t0 + u;
-          const int rr = gw * rows_per_warp + (((t >> parts_shift) << rows_per_step_shift) | rsub);
-          const int c4 = ((t & ((1 << parts_shift) - 1)) << 5) | c4_lane;
-          int k = -1;
-          if (t < steps && rr < rows) k = sidx[rr];
-          kk[u] = k;
-          if (k >= 0) {
-            e4[u] = ldg4(p.E + (int64_t)k * D + c4 * 4);
-            if (p.train) z4[u] = __ldcs(reinterpret_cast<const float4*>(zt + rr * D + c4 * 4));   // last use of this tile
-          }
-        }
+            for (int u = 0; u < U; ++u) kk[u] = sp[(t0 + u) * rps];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (kk[u] < 0) continue;
-          const int t = t0 + u;
-          const int rr = gw * rows_per_warp + (((t >> parts_shift) << rows_per_step_shift) | rsub);
-          const int c4 = ((t & ((1 << parts_shift) - 1)) << 5) | c4_lane;
-          float4 o4 = e4[u];
-          if (p.train) {
-            const float dx = __fsub_rn(e4[u].x, z4[u].x), dy = __fsub_rn(e4[u].y, z4[u].y);
-            const float dz = __fsub_rn(e4[u].z, z4[u].z), dw = __fsub_rn(e4[u].w, z4[u].w);
-            lsse = fmaf(dx, dx, lsse); lsse = fmaf(dy, dy, lsse); lsse = fmaf(dz, dz, lsse); lsse = fmaf(dw, dw, lsse);
-            o4 = make_float4(__fadd_rn(z4[u].x, dx), __fadd_rn(z4[u].y, dy), __fadd_rn(z4[u].z, dz), __fadd_rn(z4[u].w, dw));
+            for (int u = 0; u < U; ++u) {
+              e4[u] = __ldg(reinterpret_cast<const float4*>(ec + (uint32_t)(kk[u] & 0x7fffffff)));
+              if (TRAIN) z4[u] = __ldcs(reinterpret_cast<const float4*>(zp + (int64_t)((t0 + u) * rps) * D));   // last use of this tile
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              float4 o4 = e4[u];
+              if (TRAIN) {
+                const float dx = __fsub_rn(e4[u].x, z4[u].x), dy = __fsub_rn(e4[u].y, z4[u].y);
+                const float dz = __fsub_rn(e4[u].z, z4[u].z), dw = __fsub_rn(e4[u].w, z4[u].w);
+                const float ss = fmaf(dw, dw, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                lsse = fmaf(kk[u] < 0 ? 0.f : 1.f, ss, lsse);      // undecided rows are accounted by the exact kernel
+                o4 = make_float4(__fadd_rn(z4[u].x, dx), __fadd_rn(z4[u].y, dy), __fadd_rn(z4[u].z, dz), __fadd_rn(z4[u].w, dw));
+              }
+              __stcs(reinterpret_cast<float4*>(op + (int64_t)((t0 + u) * rps) * D), o4);   // streaming: never re-read
+            }
           }
-          __stcs(reinterpret_cast<float4*>(ot + rr * D + c4 * 4), o4);   // streaming: never re-read
-          if (c4 == 0) {
-            p.idx[row0 + rr] = (int64_t)kk[u];
-            if (p.train) atomicAdd(&shist[kk[u]], 1);
+        } else {
+#pragma unroll 1
+          for (int t = 0; t < nsteps; ++t) {            // last (partial) tile or odd step counts
+            const int ro = t * rps;
+            if (rbase + ro >= rows) continue;
+            const int kv = sp[ro];
+            const float4 e1 = __ldg(reinterpret_cast<const float4*>(ec + (uint32_t)(kv & 0x7fffffff)));
+            float4 o4 = e1;
+            if (TRAIN) {
+              const float4 z1 = __ldcs(reinterpret_cast<const float4*>(zp + (int64_t)ro * D));
+              const float dx = __fsub_rn(e1.x, z1.x), dy = __fsub_rn(e1.y, z1.y);
+              const float dz = __fsub_rn(e1.z, z1.z), dw = __fsub_rn(e1.w, z1.w);
+              const float ss = fmaf(dw, dw, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+              lsse = fmaf(kv < 0 ? 0.f : 1.f, ss, lsse);
+              o4 = make_float4(__fadd_rn(z1.x, dx), __fadd_rn(z1.y, dy), __fadd_rn(z1.z, dz), __fadd_rn(z1.w, dw));
+            }
+            __stcs(reinterpret_cast<float4*>(op + (int64_t)ro * D), o4);
           }
         }
       }
@@ -631,13 +681,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     if (gw != 0) { stat_acc[0] = stat_acc[1] = 0; }
 #endif
     STAT_FLUSH(2, 12);
-    // ---- CTA totals (only the gather warps touch shist after the start-up clear) ----
-    if (p.train) {
-      asm volatile("bar.sync 1, %0;" ::"r"(GATHER_WARPS * 32) : "memory");
-      for (int k = tid - GATHER_WARP0 * 32; k < K; k += GATHER_WARPS * 32) {
-        const int hcount = shist[k];
-        if (hcount) atomicAdd(p.hist + k, (unsigned long long)hcount);
-      }
+    // ---- CTA total of the squared error ----
+    if (TRAIN) {
       sse_acc = warp_sum(sse_acc);
       if (lane == 0 && sse_acc != 0.0) atomicAdd(p.sse, sse_acc);
     }
@@ -645,6 +690,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 
   tc::tc_fence_before();
   __syncthreads();
+  if (TRAIN) {   // shared-memory histogram (filled by the epilogue warps) -> global, once per CTA
+    const int* shist = reinterpret_cast<const int*>(smem + L.hist);
+    for (int k = tid; k < K; k += NTHREADS) {
+      const int hcount = shist[k];
+      if (hcount) atomicAdd(p.hist + k, (unsigned long long)hcount);
+    }
+  }
   if (tid == 0 && serr) atomicExch(p.counters + 1, serr);
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
@@ -687,9 +739,18 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   p.stats = reinterpret_cast<unsigned long long*>(counters + 8);
   p.ntiles = (N + TM - 1) / TM;
   const size_t smem = L.total + 128;
-  DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = p.ntiles < dp.sm_count ? p.ntiles : dp.sm_count;
-  vq_tc_kernel<<<(unsigned)grid, NTHREADS, smem, s>>>(p);
+#define DVQ_LAUNCH_TC(DT_, TR_)                                                                                         \
+  do {                                                                                                                 \
+    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<DT_, TR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    vq_tc_kernel<DT_, TR_><<<(unsigned)grid, NTHREADS, smem, s>>>(p);                                                  \
+  } while (0)
+  if (D == 64) {
+    if (train) DVQ_LAUNCH_TC(64, true); else DVQ_LAUNCH_TC(64, false);
+  } else {
+    if (train) DVQ_LAUNCH_TC(0, true); else DVQ_LAUNCH_TC(0, false);
+  }
+#undef DVQ_LAUNCH_TC
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return DVQ_OK;
