@@ -83,7 +83,7 @@ VqWorkspace vq_workspace_layout(int64_t N, int K, int D, int flags) {
   off = align_up(off + sizeof(int) * 64, 256);   // [0..7] counters, [8..63] optional wait-time stats
   const bool may_tc = (flags & DVQ_PATH_MASK) != DVQ_PATH_SIMT && vq_tc_supported(N, K, D);
   w.off_rowlist = off;
-  if (may_tc) off = align_up(off + sizeof(int) * (size_t)N, 256);
+  if (may_tc) off = align_up(off + 2 * align_up(sizeof(int) * (size_t)N, 256), 256);
   w.off_bop = off;
   if (may_tc) off = align_up(off + vq_tc_operand_bytes(K, D), 1024);
   w.off_rowmeta = off;
@@ -188,13 +188,18 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
     if (use_tc) {
       int* counters = reinterpret_cast<int*>(ws + w.off_counters);
       int* row_list = reinterpret_cast<int*>(ws + w.off_rowlist);
+      int* cand_list = reinterpret_cast<int*>(ws + w.off_rowlist + align_up(sizeof(int) * (size_t)N, 256));
       profile_mark(1, true, s);
-      rc = launch_vq_tc(z, E, ee, N, K, D, train, z_q, idx, hist, sse, ws + w.off_bop, counters, row_list, s);
+      rc = launch_vq_tc(z, E, ee, N, K, D, train, z_q, idx, hist, sse, ws + w.off_bop, counters, row_list, cand_list, s);
       profile_mark(1, false, s);
       if (rc) return rc;
-      // exact FP32 refine of the rows the filter flagged (device-side count, no host sync)
+      // exact FP32 refine of the rows the filter flagged (device-side count, no host sync): restricted to
+      // the recorded candidate groups when that kernel covers the shape, else the full FP32 kernel on the list
       profile_mark(2, true, s);
-      rc = launch_vq_simt(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, counters, s);
+      if (vq_refine_supported(K, D))
+        rc = launch_vq_refine(z, E, ee, K, D, train, z_q, idx, hist, sse, row_list, cand_list, counters, vq_tc_cand_gshift(K), s);
+      else
+        rc = launch_vq_simt(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, counters, s);
       profile_mark(2, false, s);
       if (rc) return rc;
     } else {

@@ -39,7 +39,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 struct VqWorkspace {
   size_t off_ee;        // float [K]            ||e_k||^2
   size_t off_counters;  // int   [8]            refine-list length, overflow flags
-  size_t off_rowlist;   // int   [N]            rows the tensor-core filter could not decide
+  size_t off_rowlist;   // int   [2][N]         rows the tensor-core filter could not decide + their candidate masks
   size_t off_bop;       // operand image of the codebook for the tcgen05 path
   size_t off_rowmeta;   // float [N]            (reserved)
   size_t total;
@@ -61,7 +61,14 @@ bool vq_tc_supported(int64_t N, int K, int D);
 size_t vq_tc_operand_bytes(int K, int D);
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
                  float* z_q, int64_t* idx, unsigned long long* hist, double* sse,
-                 void* bop, int* counters, int* row_list, cudaStream_t s);
+                 void* bop, int* counters, int* row_list, int* cand_list, cudaStream_t s);
+
+// candidate-restricted exact refine (vq_refine.cu); cand_list[i] = bit mask of 32*2^gshift-code groups
+bool vq_refine_supported(int K, int D);
+int vq_tc_cand_gshift(int K);
+int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int D, int train, float* z_q, int64_t* idx,
+                     unsigned long long* hist, double* sse, const int* row_list, const int* cand_list,
+                     const int* n_list, int gshift, cudaStream_t s);
 
 int launch_onehot(const int64_t* idx, int64_t N, int K, float* onehot, cudaStream_t s);
 int launch_finalize(const unsigned long long* hist, const double* sse, int64_t N, int K, int D, float al,

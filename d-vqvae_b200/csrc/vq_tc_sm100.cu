@@ -74,6 +74,8 @@ struct TcParams {
   double* sse;
   int* counters;   // [0] refine-list length, [1] protocol error code
   int* row_list;
+  int* cand_list;       // candidate-group mask of each listed row (bit g = codes [32*g<<gshift, ...))
+  int cand_gshift;
   uint32_t index_mask;  // 0xffffffe0 (kept in a register so key packing is one LOP3)
   unsigned long long* stats;   // optional wait-time accounting (DVQ_TC_STATS builds)
   int64_t ntiles;
@@ -97,7 +99,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   L.stage[0] = off; off += L.stage_bytes;
   L.stage[1] = off; off += L.stage_bytes;
   L.meta = off; off += META_SLOTS * TM * 4;
-  L.fin = off; off += (EPQ - 1) * TM * 12;   // (EPQ-1) helper warps x (key, col, cnt); single slot
+  L.fin = off; off += (EPQ - 1) * TM * 16;   // (EPQ-1) helper warps x (key, col, cnt, cand); single slot
   L.sidx = off; off += 2 * TM * 4;      // 2 slots of final code index (-1: undecided)
   L.hist = off; off += (uint32_t)K * 4;
   L.total = off;
@@ -241,15 +243,16 @@ __device__ __forceinline__ float half_minus_float(uint32_t h16, float a) {
   return r;
 }
 
-struct RowState {   // per (row, column-half) running result of the filter
+struct RowState {   // per (row, column subset) running result of the filter
   float m1;         // smallest key so far (index in the 5 low bits)
   float cnt;        // number of OTHER keys within `band` of m1 (a superset count)
   int col;          // global code index of m1
+  uint32_t cand;    // groups of sub-chunks holding a key within `band` of m1 (superset; always holds m1's own)
 };
 
 // One 32-column sub-chunk: keys -> FMNMX3 tree -> running minimum with exact reset -> count of keys
 // inside the band on the FMA pipe (fma.sat((T - key) * BIG) is exactly 0 or 1).
-__device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], uint32_t mask, int col0, float band, RowState& st) {
+__device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], uint32_t mask, int col0, uint32_t gbit, float band, RowState& st) {
   const float BIG = 1048576.f;
   float key[32];
 #pragma unroll
@@ -265,7 +268,7 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], uint32_t mask
   // minimum's own hit below); a smaller improvement leaves the old minimum inside the band, which the
   // new minimum's own hit accounts for.
   if (m < st.m1) {
-    if (st.m1 - m > band) st.cnt = -1.f;
+    if (st.m1 - m > band) { st.cnt = -1.f; st.cand = 0u; }
     st.m1 = m;
     st.col = col0 + (int)(__float_as_uint(m) & 31u);
   }
@@ -278,7 +281,9 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], uint32_t mask
     c2 += fma_sat(key[j + 2], -BIG, TB);
     c3 += fma_sat(key[j + 3], -BIG, TB);
   }
-  st.cnt += (c0 + c1) + (c2 + c3);
+  const float csub = (c0 + c1) + (c2 + c3);
+  st.cnt += csub;
+  if (csub > 0.5f) st.cand |= gbit;
 }
 
 // DT > 0: e_dim known at compile time (strides, trip counts and index masks become immediates and the
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int slot = (int)(it & 1);
       const uint32_t sph = (uint32_t)((it >> 1) & 1);
       RowState st;
-      st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0.f; st.col = 0;
+      st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0.f; st.col = 0; st.cand = 0u;
       float band = 0.f;
       bool ok = true;
       for (int c = 0; c < nchunks; ++c, ++q) {
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           uint32_t v[32];
           tc::tmem_ld32(tbase + (uint32_t)sc * 32u, v);
           tmem_ld_wait_dep(v);
-          filter_subchunk(v, mask, c * 256 + sc * 32, band, st);
+          filter_subchunk(v, mask, c * 256 + sc * 32, 1u << ((c * 8 + sc) >> p.cand_gshift), band, st);
         }
         tc::tc_fence_before();
         warp_arrive(&bar_acc_empty[t]);
@@ -537,11 +542,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const uint32_t fph = (uint32_t)(it & 1);
       if (wq > 0) {
         // hand this warp's partial result to the owner warp of the same rows
-        float* fin_key = fin_base + (wq - 1) * 3 * TM;
+        float* fin_key = fin_base + (wq - 1) * 4 * TM;
         { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_empty[0], fph ^ 1u, errw, ERR_FIN); STAT_ADD(1); if (!w_ok) break; }
         fin_key[r] = st.m1;
         reinterpret_cast<int*>(fin_key + TM)[r] = st.col;
         fin_key[2 * TM + r] = st.cnt;
+        reinterpret_cast<uint32_t*>(fin_key + 3 * TM)[r] = st.cand;
         warp_arrive(&bar_fin_full[0]);
       } else {
         { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_full[0], fph, errw, ERR_FIN); STAT_ADD(2); if (!w_ok) break; }
@@ -549,19 +555,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         // the winner's band (ambiguous) or voids the loser's count entirely
         float m1 = st.m1, cnt = st.cnt;
         int col = st.col;
+        uint32_t cand = st.cand;
         bool flag = false;
 #pragma unroll
         for (int h = 0; h < EPQ - 1; ++h) {
-          const float* fin_key = fin_base + h * 3 * TM;
+          const float* fin_key = fin_base + h * 4 * TM;
           const float ko = fin_key[r];
           const int co = reinterpret_cast<const int*>(fin_key + TM)[r];
           const float no = fin_key[2 * TM + r];
-          if (ko < m1) { flag = (m1 - ko <= band); m1 = ko; col = co; cnt = no; }
-          else         { flag = flag || (ko - m1 <= band); }
+          const uint32_t cando = reinterpret_cast<const uint32_t*>(fin_key + 3 * TM)[r];
+          if (ko < m1) {
+            flag = (m1 - ko <= band);
+            cand = flag ? (cand | cando) : cando;      // an improvement beyond the band voids the old candidates
+            m1 = ko; col = co; cnt = no;
+          } else if (ko - m1 <= band) {
+            flag = true;
+            cand |= cando;
+          }
         }
         warp_arrive(&bar_fin_empty[0]);
         flag = flag || (cnt > 0.5f);
-        if (band < 0.f) flag = true;
+        if (band < 0.f) { flag = true; cand = 0xffffffffu; }   // degenerate row: every group is a candidate
         const bool valid = r < rows;
         flag = flag && valid;
         { STAT_T0(); const bool w_ok = warp_wait(&bar_sidx_empty[slot], sph ^ 1u, errw, ERR_SIDX); STAT_ADD(3); if (!w_ok) break; }
@@ -579,7 +593,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           int base = 0;
           if (lane == 0) base = atomicAdd(p.counters, __popc(bal));
           base = __shfl_sync(0xffffffffu, base, 0);
-          if (flag) p.row_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)(row0 + r);
+          if (flag) {
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            p.row_list[pos] = (int)(row0 + r);
+            p.cand_list[pos] = (int)cand;
+          }
         }
       }
     }
@@ -710,13 +728,19 @@ bool vq_tc_supported(int64_t N, int K, int D) {
   return smem_layout(K, D).total + 128 + 512 <= 227 * 1024;   // + alignment slack + static barriers
 }
 
+int vq_tc_cand_gshift(int K) {   // 32 candidate bits cover K/32 sub-chunks in groups of 2^gshift
+  int g = 0;
+  while (((K + 31) / 32 + (1 << g) - 1) >> g > 32) ++g;
+  return g;
+}
+
 size_t vq_tc_operand_bytes(int K, int D) {
   return align_up(sizeof(CbMeta), 256) + align_up((size_t)smem_layout(K, D).bimg_bytes, 256);
 }
 
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,
                  int64_t* idx, unsigned long long* hist, double* sse, void* bop, int* counters, int* row_list,
-                 cudaStream_t s) {
+                 int* cand_list, cudaStream_t s) {
   DeviceProps dp;
   int rc = device_props(&dp);
   if (rc) return rc;
@@ -734,7 +758,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
 
   TcParams p;
   p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.N = N; p.K = K; p.D = D; p.train = train;
-  p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list;
+  p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list; p.cand_list = cand_list; p.cand_gshift = vq_tc_cand_gshift(K);
   p.index_mask = 0xffffffe0u;
   p.stats = reinterpret_cast<unsigned long long*>(counters + 8);
   p.ntiles = (N + TM - 1) / TM;

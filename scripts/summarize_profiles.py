@@ -55,7 +55,7 @@ def full(tag, rep):
     hdr, units = rows[0], rows[1]
     for vals in rows[2:]:
         d = dict(zip(hdr, zip(units, vals)))
-        name = d["Kernel Name"][1].split("(")[0].split("::")[-1]
+        name = d["Kernel Name"][1].split("(")[0].split("<")[0].split("::")[-1].strip() or "kernel"
         with open(os.path.join(OUT, "%s_%s_ncu.md" % (tag, name)), "w") as f:
             f.write("# %s — `ncu --set full --clock-control none` of `%s`\n\n| metric | unit | value |\n|---|---|---|\n" % (tag, d["Kernel Name"][1][:100]))
             for k in WANT:
