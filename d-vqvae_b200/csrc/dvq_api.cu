@@ -242,7 +242,7 @@ int dvq_vq_read_counters(const void* workspace, int64_t N, int K, int D, int fla
 int dvq_vq_finalize(const unsigned long long* hist, const double* sse, int64_t N_total, int K, int D, float al,
                     float beta, float* loss, float* perplexity, void* stream) {
   if (!hist || !sse || !loss || !perplexity) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
-  if (N_total <= 0 || K <= 0 || D <= 0) return fail(DVQ_ERR_BAD_SHAPE, "need N_total, K, D > 0");
+  if (N_total < 0 || K <= 0 || D <= 0) return fail(DVQ_ERR_BAD_SHAPE, "need N_total >= 0 (0 = take the histogram total), K, D > 0");
   int rc = require_sm100();
   if (rc) return rc;
   return launch_finalize(hist, sse, N_total, K, D, al, beta, loss, perplexity, static_cast<cudaStream_t>(stream));

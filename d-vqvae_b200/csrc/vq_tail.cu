@@ -33,23 +33,43 @@ __global__ void onehot_kernel_s(const int64_t* __restrict__ idx, int64_t N, int 
 }
 
 __global__ void finalize_kernel(const unsigned long long* __restrict__ hist, const double* __restrict__ sse,
-                                int64_t N, int K, int D, float al, float beta, float* __restrict__ loss,
+                                int64_t N_arg, int K, int D, float al, float beta, float* __restrict__ loss,
                                 float* __restrict__ ppl) {
   __shared__ double red[32];
+  __shared__ double s_n;
+  // N_arg == 0: the global row count is the histogram total (every row is counted exactly once), so a
+  // row-sharded caller needs no second collective for it
+  if (N_arg > 0) {
+    if (threadIdx.x == 0) s_n = (double)N_arg;
+  } else {
+    double c = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) c += (double)hist[k];
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+      s_n = t;
+    }
+  }
+  __syncthreads();
+  const double n = s_n;
   double s = 0.0;
-  const double inv_n = 1.0 / (double)N;
+  const double inv_n = 1.0 / n;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const double p = (double)hist[k] * inv_n;
     s += p * log(p + 1e-10);
   }
   s = warp_sum(s);
+  __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     *ppl = (float)exp(-t);
-    const float m = (float)(*sse / ((double)N * (double)D));
+    const float m = (float)(*sse / (n * (double)D));
     *loss = __fadd_rn(__fmul_rn(al, m), __fmul_rn(beta, m));
   }
 }

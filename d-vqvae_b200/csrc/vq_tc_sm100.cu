@@ -83,13 +83,16 @@ struct TcParams {
 
 struct SmemLayout {
   uint32_t bimg, a_img[2], stage[2], meta, fin, sidx, hist, total;
-  uint32_t bimg_bytes, a_bytes, stage_bytes;
+  uint32_t bimg_bytes, a_bytes, stage_bytes;   // bimg_bytes: the 2-slot codebook ring in shared memory
+  uint32_t bchunk_bytes, hist_in_smem;           // one 256-code chunk of the operand image
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   SmemLayout L;
   const uint32_t kc_b = (uint32_t)(D + 16) / 8, kc_a = (uint32_t)(2 * D + 16) / 8;
-  L.bimg_bytes = kc_b * (uint32_t)K * 16;
+  L.bchunk_bytes = kc_b * 256u * 16u;
+  L.bimg_bytes = 2u * L.bchunk_bytes;
+  L.hist_in_smem = K <= 512 ? 1u : 0u;   // larger histograms go straight to global atomics (shared memory is full)
   L.a_bytes = kc_a * A_CHUNK_BYTES;
   L.stage_bytes = (uint32_t)TM * D * 4;
   uint32_t off = 0;
@@ -101,7 +104,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   L.meta = off; off += META_SLOTS * TM * 4;
   L.fin = off; off += (EPQ - 1) * TM * 16;   // (EPQ-1) helper warps x (key, col, cnt, cand); single slot
   L.sidx = off; off += 2 * TM * 4;      // 2 slots of final code index (-1: undecided)
-  L.hist = off; off += (uint32_t)K * 4;
+  L.hist = off; off += L.hist_in_smem ? (uint32_t)K * 4 : 0u;
   L.total = off;
   return L;
 }
@@ -140,6 +143,13 @@ __global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, CbMeta* 
   }
 }
 
+// byte offset of element (code k, column d) in the global operand image: chunk-contiguous
+// [k / 256][d / 8][k % 256][d % 8] halfs, i.e. each 256-code chunk is one contiguous shared-memory image
+__host__ __device__ inline size_t bimg_offset(int k, int d, int D) {
+  const size_t chunk_bytes = (size_t)((D + 16) / 8) * 256 * 16;
+  return (size_t)(k >> 8) * chunk_bytes + (size_t)(d >> 3) * (256 * 16) + (size_t)(k & 255) * 16 + (size_t)(d & 7) * 2;
+}
+
 // one warp per code: eh = fp16(-2 s_E e), fold columns, residual norm -> atomic max
 __global__ void tc_cb_image_kernel(const float* __restrict__ E, const float* __restrict__ ee, int K, int D,
                                    CbMeta* __restrict__ cb, uint8_t* __restrict__ bimg) {
@@ -153,7 +163,7 @@ __global__ void tc_cb_image_kernel(const float* __restrict__ E, const float* __r
     const __half h = __float2half_rn(v);
     const float r = v - __half2float(h);       // exact
     res = fmaf(r, r, res);
-    *reinterpret_cast<__half*>(bimg + (size_t)(d >> 3) * K * 16 + (size_t)warp * 16 + (d & 7) * 2) = h;
+    *reinterpret_cast<__half*>(bimg + bimg_offset(warp, d, D)) = h;
   }
   res = warp_sum(res);
   if (lane < 16) {   // fold k-chunks D/8 and D/8+1
@@ -167,7 +177,7 @@ __global__ void tc_cb_image_kernel(const float* __restrict__ E, const float* __r
     if (lane == 2) v = mid;
     if (lane == 3) v = lo;
     const int d = D + lane;
-    *reinterpret_cast<__half*>(bimg + (size_t)(d >> 3) * K * 16 + (size_t)warp * 16 + (d & 7) * 2) = __float2half_rn(v);
+    *reinterpret_cast<__half*>(bimg + bimg_offset(warp, d, D)) = __float2half_rn(v);
   }
   if (lane == 0) atomicMax(reinterpret_cast<int*>(&cb->delta_max), __float_as_int(sqrtf(res) * (1.f + 1e-5f)));
 }
@@ -291,7 +301,7 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], uint32_t mask
 template <int DT, bool TRAIN>
 __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_stage_full[2], bar_stage_empty[2], bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2], bar_b_full;
+  __shared__ uint64_t bar_stage_full[2], bar_stage_empty[2], bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2], bar_b_full[2], bar_b_empty[2];
   __shared__ uint64_t bar_fin_full[2], bar_fin_empty[2], bar_sidx_full[2], bar_sidx_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int serr;
@@ -317,11 +327,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       tc::mbar_init(&bar_fin_empty[i], 4);
       tc::mbar_init(&bar_sidx_full[i], 4);      // half-0 epilogue warps -> gather warps
       tc::mbar_init(&bar_sidx_empty[i], GATHER_WARPS);
+      tc::mbar_init(&bar_b_full[i], 1);
+      tc::mbar_init(&bar_b_empty[i], 1);
     }
-    tc::mbar_init(&bar_b_full, 1);
     tc::fence_barrier_init();
   }
-  {
+  if (L.hist_in_smem) {
     int* shist = reinterpret_cast<int*>(smem + L.hist);
     for (int k = tid; k < K; k += NTHREADS) shist[k] = 0;
   }
@@ -335,11 +346,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&bar_b_full, L.bimg_bytes);
-      for (uint32_t off = 0; off < L.bimg_bytes; off += 16384) {
-        const uint32_t n = min(16384u, L.bimg_bytes - off);
-        tc::bulk_g2s(smem + L.bimg + off, p.bimg + off, n, &bar_b_full);
+      // codebook operand image: K <= 512 stays resident in the two ring slots; larger codebooks are
+      // streamed chunk by chunk (256 codes) for every row tile from L2
+      const bool resident = nchunks <= 2;
+      auto load_chunk = [&](int c, int slot) {
+        const uint32_t bytes = (uint32_t)(((uint32_t)(D + 16) / 8u) * 256u * 16u);
+        const uint8_t* src = p.bimg + (size_t)c * bytes;
+        tc::mbar_arrive_expect_tx(&bar_b_full[slot], bytes);
+        for (uint32_t off = 0; off < bytes; off += 16384) {
+          const uint32_t n = min(16384u, bytes - off);
+          tc::bulk_g2s(smem + L.bimg + (uint32_t)slot * L.bchunk_bytes + off, src + off, n, &bar_b_full[slot]);
+        }
+      };
+      if (resident) {
+        for (int c = 0; c < nchunks; ++c) load_chunk(c, c);
       }
+      uint32_t qb = 0;   // running chunk counter of the streamed ring
       STAT_DECL(1);
       for (int64_t it = 0; it < my_tiles; ++it) {
         const int64_t tile = blockIdx.x + it * gridDim.x;
@@ -352,14 +374,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         tc::mbar_arrive_expect_tx(&bar_stage_full[s], bytes);
         if (TRAIN) tc::bulk_g2s_keep(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
         else tc::bulk_g2s(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
+        if (!resident) {
+          for (int c = 0; c < nchunks; ++c, ++qb) {
+            const int slot = (int)(qb & 1u);
+            if (!tc::mbar_wait(&bar_b_empty[slot], ((qb >> 1) & 1u) ^ 1u, errw, ERR_B_FULL)) break;
+            load_chunk(c, slot);
+          }
+        }
       }
       STAT_FLUSH(1, 0);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      bool ok = tc::mbar_wait(&bar_b_full, 0, errw, ERR_B_FULL);
-      const uint32_t b_lbo = (uint32_t)K * 16, b_sbo = 128;
+      bool ok = true;
+      const bool resident = nchunks <= 2;
+      if (resident) for (int c = 0; c < nchunks; ++c) ok = ok && tc::mbar_wait(&bar_b_full[c], 0, errw, ERR_B_FULL);
+      const uint32_t b_lbo = 256u * 16u, b_sbo = 128;
       const uint32_t a_lbo = A_CHUNK_BYTES, a_sbo = 128;
       // descriptors are (address >> 4) in the low bits: advancing by one k-step (two 8-wide k-chunks)
       // is a constant add that never carries out of the 14-bit address field
@@ -383,7 +414,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           const int n = min(256, K - c * 256);
           const uint32_t idesc = tc::make_idesc_f16(128, n, 0);
           const uint32_t d_tmem = tmem_base + t * 256u;
-          const uint64_t bc = b_desc0 + (uint64_t)((uint32_t)c * 256u);     // 256 codes * 16 B >> 4
+          const uint32_t bslot = resident ? (uint32_t)c : (q & 1u);
+          if (!resident) {
+            if (!tc::mbar_wait(&bar_b_full[bslot], (q >> 1) & 1u, errw, ERR_B_FULL)) { ok = false; break; }
+          }
+          const uint64_t bc = b_desc0 + (uint64_t)((bslot * L.bchunk_bytes) >> 4);
           uint64_t ad = a ? a_desc0[1] : a_desc0[0], bd = bc;
           uint32_t acc = 0;
 #pragma unroll 1
@@ -399,6 +434,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           }
           tc::umma_f16(d_tmem, ad, bd, idesc, 1);   // fold columns
           tc::umma_commit(&bar_acc_full[t]);
+          if (!resident) tc::umma_commit(&bar_b_empty[bslot]);   // ring slot free once these MMAs have read it
         }
         tc::umma_commit(&bar_a_empty[a]);
       }
@@ -585,7 +621,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         warp_arrive(&bar_sidx_full[slot]);
         if (valid && !flag) {
           p.idx[row0 + r] = (int64_t)col;          // 32 lanes x 8 B: one coalesced 256-byte store per warp
-          if (TRAIN) atomicAdd(reinterpret_cast<int*>(smem + L.hist) + col, 1);
+          if (TRAIN) {
+            if (L.hist_in_smem) atomicAdd(reinterpret_cast<int*>(smem + L.hist) + col, 1);
+            else atomicAdd(p.hist + col, 1ull);   // large codebooks: contention is low, shared memory is full
+          }
         }
         // undecided rows -> list for the exact FP32 kernel (one atomic per warp that has any)
         const unsigned bal = __ballot_sync(0xffffffffu, flag);
@@ -708,7 +747,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 
   tc::tc_fence_before();
   __syncthreads();
-  if (TRAIN) {   // shared-memory histogram (filled by the epilogue warps) -> global, once per CTA
+  if (TRAIN && L.hist_in_smem) {   // shared-memory histogram (filled by the epilogue warps) -> global, once per CTA
     const int* shist = reinterpret_cast<const int*>(smem + L.hist);
     for (int k = tid; k < K; k += NTHREADS) {
       const int hcount = shist[k];
@@ -724,7 +763,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 bool vq_tc_supported(int64_t N, int K, int D) {
   if (N <= 0 || N > 2147483647LL - 256) return false;
   if (D < 16 || D > 256 || (D & (D - 1)) != 0) return false;   // power of two: index math is masks/shifts
-  if (K % 32 != 0 || K < 32 || K > 4096) return false;
+  if (K % 32 != 0 || K < 32 || K > 32768) return false;
   return smem_layout(K, D).total + 128 + 512 <= 227 * 1024;   // + alignment slack + static barriers
 }
 
@@ -735,7 +774,7 @@ int vq_tc_cand_gshift(int K) {   // 32 candidate bits cover K/32 sub-chunks in g
 }
 
 size_t vq_tc_operand_bytes(int K, int D) {
-  return align_up(sizeof(CbMeta), 256) + align_up((size_t)smem_layout(K, D).bimg_bytes, 256);
+  return align_up(sizeof(CbMeta), 256) + align_up((size_t)((K + 255) / 256) * smem_layout(K, D).bchunk_bytes, 256);
 }
 
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,
@@ -751,7 +790,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   const SmemLayout L = smem_layout(K, D);
   tc_cb_stats_kernel<<<1, 256, 0, s>>>(ee, K, cb, counters);
   DVQ_CUDA_CHECK(cudaGetLastError());
-  DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, L.bimg_bytes, s));
+  DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, (size_t)((K + 255) / 256) * L.bchunk_bytes, s));
   tc_cb_image_kernel<<<(K * 32 + 255) / 256, 256, 0, s>>>(E, ee, K, D, cb, bimg);
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch(2);

@@ -33,7 +33,8 @@ def _nccl_comm_ptr(group, device):
 
 def allreduce_stats(stats: torch.Tensor, n_e: int, n_local: int, group=None) -> int:
     """In-place sum over ranks of ``stats = [hist (n_e x int64 bit-pattern of uint64) | sse (float64 bits)]``.
-    Returns the global row count (sum of ``n_local``)."""
+    Returns the row count to hand to ``dvq_vq_finalize``: ``n_local`` on one rank, else 0 ("use the
+    histogram total" — every row is counted once, so no second collective and no host sync)."""
     if group is None:
         group = tdist.group.WORLD
     world = tdist.get_world_size(group)
@@ -54,11 +55,7 @@ def allreduce_stats(stats: torch.Tensor, n_e: int, n_local: int, group=None) -> 
     if not done:
         tdist.all_reduce(hist, op=tdist.ReduceOp.SUM, group=group)
         tdist.all_reduce(sse, op=tdist.ReduceOp.SUM, group=group)
-    # global row count: the histogram sums to it, so no second message is needed when every
-    # row was counted; ranks may hold different shard sizes
-    n = torch.tensor([int(n_local)], dtype=torch.int64, device=stats.device)
-    tdist.all_reduce(n, op=tdist.ReduceOp.SUM, group=group)
-    return int(n.item())
+    return 0
 
 
 def shard_module(module, group=None):

@@ -97,7 +97,8 @@ DVQ_API int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int
 DVQ_API int dvq_vq_read_counters(const void* workspace, int64_t N, int K, int D, int flags, int* out4);
 
 /* loss = al*mean((z_q-z)^2) + beta*mean((z_q-z)^2) (quantizer.py:56-57),
- * perplexity = exp(-sum p log(p+1e-10)), p = hist/N_total (:63-64). */
+ * perplexity = exp(-sum p log(p+1e-10)), p = hist/N_total (:63-64).  N_total == 0 means "use the
+ * histogram total" (every row is counted once), which spares a row-sharded caller a second collective. */
 DVQ_API int dvq_vq_finalize(const unsigned long long* hist, const double* sse, int64_t N_total, int K, int D,
                     float al, float beta, float* loss, float* perplexity, void* stream);
 

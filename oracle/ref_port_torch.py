@@ -100,7 +100,7 @@ def pointnet_eval(x: torch.Tensor, sd: dict):
     g = F.relu(_bn_eval(F.linear(g, sd["stn.fc2.weight"], sd["stn.fc2.bias"]),
                         sd["stn.bn5.weight"], sd["stn.bn5.bias"], sd["stn.bn5.running_mean"], sd["stn.bn5.running_var"]))
     g = F.linear(g, sd["stn.fc3.weight"], sd["stn.fc3.bias"])
-    trans = (g + torch.eye(3).view(1, 9)).view(-1, 3, 3)
+    trans = (g + torch.eye(3, device=g.device).view(1, 9)).view(-1, 3, 3)
     xt = x.transpose(2, 1)
     xyz = torch.bmm(xt[:, :, :3], trans)
     xt = torch.cat([xyz, xt[:, :, 3:]], dim=2) if C > 3 else xyz

@@ -55,7 +55,8 @@ if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)
     rep = {}
     for cfg in [(128, 32, 16, "default"), (1000, 512, 64, "default"), (65536, 512, 64, "default"), (65536, 512, 64, "variant_b"),
-                (4194304, 512, 64, "default"), (4194304, 512, 64, "variant_b"), (300000, 256, 32, "default"), (100000, 1024, 16, "default")]:
+                (4194304, 512, 64, "default"), (4194304, 512, 64, "variant_b"), (300000, 256, 32, "default"), (100000, 1024, 16, "default"),
+                (262144, 4096, 64, "default"), (262144, 4096, 64, "variant_b"), (65536, 16384, 64, "default"), (100000, 1536, 32, "default"), (50000, 800, 64, "default")]:
         try:
             rep[str(cfg)] = run(*cfg)
         except Exception as e:

@@ -39,7 +39,9 @@ def _worker(rank, world, port, name, out):
     stats = torch.zeros(E.shape[0] + 1, dtype=torch.int64)
     stats[:E.shape[0]] = torch.from_numpy(hist)
     stats[E.shape[0]:].view(torch.float64)[0] = sse
-    n_total = ddist.allreduce_stats(stats, E.shape[0], hi - lo)
+    n_flag = ddist.allreduce_stats(stats, E.shape[0], hi - lo)
+    assert n_flag == 0                                               # "take the histogram total"
+    n_total = int(stats[:E.shape[0]].sum())
     g_hist = stats[:E.shape[0]].numpy().copy()
     g_sse = float(stats[E.shape[0]:].view(torch.float64)[0])
     out[rank] = (lo, hi, n_total, g_hist, g_sse, idx)

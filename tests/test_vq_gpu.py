@@ -230,3 +230,36 @@ def test_host_buffer_entry_equals_device_entry(train):
             idx, zq = m(zt.cuda(), False)
     assert torch.equal(idx_h, idx.cpu()) and torch.equal(zq_h, zq.cpu())
     hq.close()
+
+
+@pytest.mark.parametrize("K,D", [(800, 64), (4096, 64), (1536, 32), (16384, 64)])
+@pytest.mark.parametrize("variant", ["default", "variant_b"])
+def test_streamed_codebook_tc_path(K, D, variant):
+    """Codebooks larger than the shared-memory-resident limit are streamed chunk by chunk through the
+    tcgen05 kernel: parity against the all-FP32 kernel and the oracle (band rule), ragged N."""
+    from dvq import _cabi
+    N = 20000 + 37
+    if variant == "default":
+        E = vo.default_codebook(K, D, 31)
+        z = vo.normal_latents(N, D, 32)
+    else:
+        z, E = vo.variant_b(N, K, D, 33)
+    out = {}
+    for name, path in (("simt", _cabi.DVQ_PATH_SIMT), ("tc", _cabi.DVQ_PATH_TC)):
+        m = _module(E, 1.0, 0.25, path)
+        m.onehot_limit_bytes = 0
+        with torch.no_grad():
+            out[name] = m(torch.from_numpy(z).cuda(), True) + (m.last_stats.clone(),)
+        assert m.last_counters(N)[1] == 0                       # no pipeline protocol error
+    (ls, qs, ps, _, is_, ss), (lt, qt, pt, _, it, st) = out["simt"], out["tc"]
+    idx_t, idx_s = it.cpu().numpy(), is_.cpu().numpy()
+    n_mis, n_bad, worst = vo.allowed_index_mismatch(z, E, idx_t, idx_s)
+    assert n_bad == 0, (n_mis, worst)
+    ridx, _ = vo.forward_infer(z, E)
+    assert vo.allowed_index_mismatch(z, E, idx_t, ridx)[1] == 0
+    assert np.array_equal(qt.cpu().numpy().view(np.uint32), vo.zq_train_from_idx(z, E, idx_t).view(np.uint32))
+    hist = np.bincount(idx_t.reshape(-1), minlength=K)
+    assert np.array_equal(st[:K].cpu().numpy(), hist)
+    assert rel_err(lt.item(), ls.item()) < REL
+    if n_mis == 0:
+        assert rel_err(pt.item(), ps.item()) < REL
