@@ -1,0 +1,46 @@
+"""GPU: the batched grasp-generation graph (GenNet.gen restated around the B200 modules) against a
+stage-by-stage recomputation with the oracle on the same weights, codes and hand stub."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pointnet_oracle as po
+from oracle import vq_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+
+def test_grasp_pipeline_matches_oracle_stages():
+    import dvq
+    torch.manual_seed(0)
+    net = dvq.GraspGenerator().cuda().eval()
+    for name in ("obj_encoder_type", "obj_encoder_pos"):
+        getattr(net, name).load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in po.make_state(hash(name) % 1000, 4).items()})
+    net.recon_encoder.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in po.make_state(77, 3).items()})
+    x = po.make_cloud(9, 5, 4, 777)
+    recon, pos = net.gen(torch.from_numpy(x).cuda())
+    assert tuple(recon.shape) == (5, 55) and tuple(pos.shape) == (5, 6)
+    L = net.last
+    sd_t = {k: v.detach().cpu().numpy() for k, v in net.obj_encoder_type.state_dict().items()}
+    rf, _, _ = po.pointnet_forward(x, sd_t)
+    assert np.abs(L["feat_type"].cpu().numpy() - rf).max() <= 5e-5 * np.abs(rf).max()
+    E6 = net.vqvae6.vector_quantization.embedding.weight.detach().cpu().numpy()
+    ridx, rzq = vo.forward_infer(L["feat_type"].cpu().numpy(), E6)
+    assert vo.allowed_index_mismatch(L["feat_type"].cpu().numpy(), E6, L["idx6"].cpu().numpy(), ridx)[1] == 0
+    assert np.array_equal(L["obj_emb"].cpu().numpy().view(np.uint32), E6[L["idx6"].cpu().numpy().reshape(-1)].view(np.uint32))
+    codes = L["codes"].cpu().numpy()
+    embs = [getattr(net, "vqvae%d" % i).vector_quantization.embedding.weight.detach().cpu().numpy()[codes[:, i]] for i in range(6)]
+    z_out = torch.from_numpy(np.concatenate(embs + [L["feat_type"].cpu().numpy()], axis=1))
+    ref_recon = net.decoder.cpu()(z_out)
+    assert torch.allclose(recon.cpu(), ref_recon, rtol=1e-4, atol=1e-5)
+    sd_r = {k: v.detach().cpu().numpy() for k, v in net.recon_encoder.state_dict().items()}
+    hf, _, _ = po.pointnet_forward(np.ascontiguousarray(L["verts"].permute(0, 2, 1).cpu().numpy()), sd_r)
+    assert np.abs(L["hand_feat"].cpu().numpy() - hf).max() <= 5e-5 * np.abs(hf).max()
+
+
+def test_grasp_state_dict_names_follow_reference():
+    import dvq
+    keys = set(dvq.GraspGenerator().state_dict())
+    for k in ("obj_encoder_type.stn.conv1.weight", "vqvae0.vector_quantization.embedding.weight", "vqvae6.vector_quantization.embedding.weight",
+              "decoder.MLP.L0.weight", "decoder.MLP.L2.bias", "recon_encoder.bn3.running_var", "pos_decoder.MLP.L1.weight"):
+        assert k in keys, k
