@@ -275,24 +275,38 @@ int dvq_onehot(const int64_t* idx, int64_t N, int K, float* out, void* stream) {
   return launch_onehot(idx, N, K, out, static_cast<cudaStream_t>(stream));
 }
 
-int dvq_pointnet_workspace_bytes(int B, int C, int P, size_t* bytes) {
-  if (!bytes) return fail(DVQ_ERR_BAD_ARG, "bytes is NULL");
+static int check_pn_shape(int B, int C, int P) {
   if (B < 0 || P <= 0 || (C != 3 && C != 4)) return fail(DVQ_ERR_BAD_SHAPE, "need B >= 0, P > 0, C in {3,4} (got B=%d C=%d P=%d)", B, C, P);
-  *bytes = pointnet_workspace_bytes(B, C, P);
   return DVQ_OK;
+}
+
+int dvq_pointnet_workspace_bytes_ex(int B, int C, int P, int flags, size_t* bytes) {
+  if (!bytes) return fail(DVQ_ERR_BAD_ARG, "bytes is NULL");
+  int rc = check_pn_shape(B, C, P);
+  if (rc) return rc;
+  *bytes = pointnet_workspace_bytes(B, C, P, flags);
+  return DVQ_OK;
+}
+
+int dvq_pointnet_workspace_bytes(int B, int C, int P, size_t* bytes) { return dvq_pointnet_workspace_bytes_ex(B, C, P, 0, bytes); }
+
+int dvq_pointnet_forward_ex(const float* x, const DvqPointNetWeights* w, int B, int C, int P, int flags, float* feat,
+                            float* trans, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_pn_shape(B, C, P);
+  if (rc) return rc;
+  if (!w) return fail(DVQ_ERR_BAD_ARG, "weights struct is NULL");
+  if (B > 0 && (!x || !feat || !trans || !workspace)) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
+  if (workspace_bytes < pointnet_workspace_bytes(B, C, P, flags))
+    return fail(DVQ_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, pointnet_workspace_bytes(B, C, P, flags));
+  rc = require_sm100();
+  if (rc) return rc;
+  if (B == 0) return DVQ_OK;
+  return launch_pointnet(x, w, B, C, P, flags, feat, trans, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int dvq_pointnet_forward(const float* x, const DvqPointNetWeights* w, int B, int C, int P, float* feat, float* trans,
                          void* workspace, size_t workspace_bytes, void* stream) {
-  if (B < 0 || P <= 0 || (C != 3 && C != 4)) return fail(DVQ_ERR_BAD_SHAPE, "need B >= 0, P > 0, C in {3,4} (got B=%d C=%d P=%d)", B, C, P);
-  if (!w) return fail(DVQ_ERR_BAD_ARG, "weights struct is NULL");
-  if (B > 0 && (!x || !feat || !trans || !workspace)) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
-  if (workspace_bytes < pointnet_workspace_bytes(B, C, P))
-    return fail(DVQ_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, pointnet_workspace_bytes(B, C, P));
-  int rc = require_sm100();
-  if (rc) return rc;
-  if (B == 0) return DVQ_OK;
-  return launch_pointnet(x, w, B, C, P, feat, trans, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  return dvq_pointnet_forward_ex(x, w, B, C, P, 0, feat, trans, workspace, workspace_bytes, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

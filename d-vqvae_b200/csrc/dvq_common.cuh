@@ -80,9 +80,13 @@ int launch_umma_probe(const void* a_img, uint32_t a_bytes, const void* b_img, ui
                       const uint32_t* strides, uint32_t idesc, int n_cols, float* out, int* err, cudaStream_t s);
 
 // PointNet
-size_t pointnet_workspace_bytes(int B, int C, int P);
-int launch_pointnet(const float* x, const DvqPointNetWeights* w, int B, int C, int P, float* feat,
+size_t pointnet_workspace_bytes(int B, int C, int P, int flags);
+int launch_pointnet(const float* x, const DvqPointNetWeights* w, int B, int C, int P, int flags, float* feat,
                     float* trans, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t pointnet_tc_image_bytes();
+int launch_pointnet_tc_trunk(const float* x, const float* trans, const float* w1, const float* b1, const float* w2,
+                             const float* b2, const float* w3, int B, int C, int P, float* maxbuf, void* images,
+                             bool main_trunk, cudaStream_t s);
 
 // ---- small device helpers ----------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

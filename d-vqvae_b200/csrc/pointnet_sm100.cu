@@ -259,50 +259,57 @@ stn_head_kernel(const float* __restrict__ g /* [B,1024] = relu(max+b3) */, DvqPo
 
 }  // namespace
 
-// workspace: maxbuf_stn [B,1024] | maxbuf_main [B,1024] | g [B,1024]
-size_t pointnet_workspace_bytes(int B, int C, int P) {
+// workspace: maxbuf_stn [B,1024] | maxbuf_main [B,1024] | g [B,1024] | (tensor-core path) FP16 weight images
+size_t pointnet_workspace_bytes(int B, int C, int P, int flags) {
   (void)C; (void)P;
-  return align_up(sizeof(float) * 1024 * (size_t)B, 256) * 3;
+  return align_up(sizeof(float) * 1024 * (size_t)B, 256) * 3 + ((flags & DVQ_PN_FP16_TC) ? align_up(pointnet_tc_image_bytes(), 256) : 0);
 }
 
-int launch_pointnet(const float* x, const DvqPointNetWeights* w, int B, int C, int P, float* feat, float* trans,
+int launch_pointnet(const float* x, const DvqPointNetWeights* w, int B, int C, int P, int flags, float* feat, float* trans,
                     void* ws, size_t ws_bytes, cudaStream_t s) {
   (void)ws_bytes;
   DeviceProps dp;
   int rc = device_props(&dp);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DVQ_CUDA_CHECK(cudaFuncSetAttribute(pointnet_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrunkSmem));
-    DVQ_CUDA_CHECK(cudaFuncSetAttribute(pointnet_trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrunkSmem));
-    attr_set = true;
-  }
+  DVQ_CUDA_CHECK(cudaFuncSetAttribute(pointnet_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrunkSmem));
+  DVQ_CUDA_CHECK(cudaFuncSetAttribute(pointnet_trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrunkSmem));
   const size_t stride = align_up(sizeof(float) * 1024 * (size_t)B, 256);
   float* max_stn = reinterpret_cast<float*>(static_cast<char*>(ws));
   float* max_main = reinterpret_cast<float*>(static_cast<char*>(ws) + stride);
   float* g = reinterpret_cast<float*>(static_cast<char*>(ws) + 2 * stride);
+  void* images = static_cast<char*>(ws) + 3 * stride;
+  const bool tcp = (flags & DVQ_PN_FP16_TC) != 0;
   const int64_t nfeat = (int64_t)B * 1024;
   const int ptiles = (P + PT - 1) / PT;
-  const int fill_blocks = (int)((2 * stride / 4 + 255) / 256 < (size_t)dp.sm_count * 8 ? (2 * stride / 4 + 255) / 256 : (size_t)dp.sm_count * 8);
-  fill_kernel<<<fill_blocks, 256, 0, s>>>(max_stn, (int64_t)(2 * stride / 4), -INFINITY);
-  DVQ_CUDA_CHECK(cudaGetLastError());
-  count_launch();
-
-  TrunkWeights ts = {w->stn_w1, w->stn_b1, w->stn_w2, w->stn_b2, w->stn_w3};
-  pointnet_trunk_kernel<false><<<(unsigned)((int64_t)B * ptiles), NTHREADS, kTrunkSmem, s>>>(x, ts, nullptr, B, C, P, ptiles, max_stn);
-  DVQ_CUDA_CHECK(cudaGetLastError());
-  count_launch();
   const int dec_blocks = (int)((nfeat + 255) / 256 < (int64_t)dp.sm_count * 8 ? (nfeat + 255) / 256 : (int64_t)dp.sm_count * 8);
+  if (tcp) {
+    rc = launch_pointnet_tc_trunk(x, nullptr, w->stn_w1, w->stn_b1, w->stn_w2, w->stn_b2, w->stn_w3, B, C, P, max_stn, images, false, s);
+    if (rc) return rc;
+  } else {
+    const int fill_blocks = (int)((2 * stride / 4 + 255) / 256 < (size_t)dp.sm_count * 8 ? (2 * stride / 4 + 255) / 256 : (size_t)dp.sm_count * 8);
+    fill_kernel<<<fill_blocks, 256, 0, s>>>(max_stn, (int64_t)(2 * stride / 4), -INFINITY);
+    DVQ_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    TrunkWeights ts = {w->stn_w1, w->stn_b1, w->stn_w2, w->stn_b2, w->stn_w3};
+    pointnet_trunk_kernel<false><<<(unsigned)((int64_t)B * ptiles), NTHREADS, kTrunkSmem, s>>>(x, ts, nullptr, B, C, P, ptiles, max_stn);
+    DVQ_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
   decode_kernel<<<dec_blocks, 256, 0, s>>>(max_stn, w->stn_b3, nfeat, 1, g);
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch();
   stn_head_kernel<<<(B + HB - 1) / HB, 256, 0, s>>>(g, *w, B, trans);
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch();
-  TrunkWeights tm = {w->w1, w->b1, w->w2, w->b2, w->w3};
-  pointnet_trunk_kernel<true><<<(unsigned)((int64_t)B * ptiles), NTHREADS, kTrunkSmem, s>>>(x, tm, trans, B, C, P, ptiles, max_main);
-  DVQ_CUDA_CHECK(cudaGetLastError());
-  count_launch();
+  if (tcp) {
+    rc = launch_pointnet_tc_trunk(x, trans, w->w1, w->b1, w->w2, w->b2, w->w3, B, C, P, max_main, images, true, s);
+    if (rc) return rc;
+  } else {
+    TrunkWeights tm = {w->w1, w->b1, w->w2, w->b2, w->w3};
+    pointnet_trunk_kernel<true><<<(unsigned)((int64_t)B * ptiles), NTHREADS, kTrunkSmem, s>>>(x, tm, trans, B, C, P, ptiles, max_main);
+    DVQ_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
   decode_kernel<<<dec_blocks, 256, 0, s>>>(max_main, w->b3, nfeat, 0, feat);
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch();

@@ -1,0 +1,323 @@
+// tcgen05 PointNet trunk: the shared MLP C -> 64 -> 128 -> 1024 + max-pool over the point set with the
+// 64->128 and 128->1024 layers (99.8 % of the flops) on the 5th-generation tensor cores, FP16 operands
+// (the same 10-bit mantissa as the TF32 cuDNN path the reference takes on a GPU), FP32 accumulation in
+// TMEM.  Replaces network/pointnet_encoder.py:29-32 (STN trunk) and :150-164 (main trunk).
+//
+// Work split: CTA = (group of clouds, quarter of the 1024 output channels).  The CTA keeps its quarter
+// of the layer-3 weights (256 x 128 fp16 = 64 KB) and all of layer 2 (128 x 80 fp16 incl. the bias
+// fold column) resident in shared memory as UMMA operand images and walks over 256-point tiles:
+//   L1  (CUDA cores, thread = point): coalesced point-major load of x[b, :, p0:p0+256], optional 3x3
+//       input transform, 4 -> 64 in FP32, ReLU fused into the FP16 pack (cvt.rn.relu.f16x2.f32),
+//       rows written straight into the K-major A image of layer 2 (+ a 1.0 column for the bias).
+//   L2  tcgen05.mma: D2[point, channel] = h1 . W2^T (M = 128 points x 2 halves, N = 128, K = 80);
+//       epilogue: thread = point reads its 128 channels from TMEM, ReLU + FP16 pack, writes its row of
+//       the K-major B image of layer 3 (16 conflict-free 128-bit stores).
+//   L3  tcgen05.mma: D3[channel, point] = W3 . h2^T (M = 128 channels, N = 128 points, K = 128), so the
+//       max over the point set is a THREAD-LOCAL 3-input max along the TMEM columns of each lane; the
+//       per-channel running maximum lives in registers across all tiles of the cloud and is written
+//       once (no atomics).  Points beyond P replicate the last valid point, which leaves the max intact.
+// Bias (and the STN's ReLU) of layer 3 commute with the max and are applied by decode_kernel.
+// Layers 1-2 are recomputed by the 4 channel-quarter CTAs (6 % of the flops) — cheaper than streaming
+// 256 KB of layer-3 weights per tile from L2.
+//
+// Roofline: tensor pipe; algorithmic 2 * 139 520 flop per point per trunk, 16 * P bytes in + 4 KB out
+// per cloud.  Phases inside a CTA are serialised by __syncthreads in this version (L1 / L2 / L3 do not
+// overlap yet), see DESIGN.md.
+#include <cuda_fp16.h>
+
+#include "dvq_common.cuh"
+#include "tc_prims.cuh"
+
+namespace dvq {
+namespace {
+
+constexpr int PT = 256;                 // points per tile
+constexpr int NT = 256;                 // threads per CTA (thread <-> point in L1 / L2 epilogue)
+constexpr int K1 = 80;                  // layer-2 contraction length: 64 channels + 16 fold columns
+constexpr int KC1 = K1 / 8;             // 8-wide k-chunks of the layer-2 operands
+constexpr int KC2 = 128 / 8;            // k-chunks of the layer-3 operands
+
+// shared memory (bytes); every operand image is [k-chunk][row][16 B] (K-major, no swizzle)
+constexpr uint32_t W3Q_BYTES = KC2 * 256 * 16;   // 64 KB: 256 channels of this quarter
+constexpr uint32_t W2_BYTES = KC1 * 128 * 16;    // 20 KB
+constexpr uint32_t H1_BYTES = KC1 * PT * 16;     // 40 KB
+constexpr uint32_t H2_BYTES = KC2 * PT * 16;     // 64 KB
+constexpr uint32_t OFF_W3Q = 0;
+constexpr uint32_t OFF_W2 = OFF_W3Q + W3Q_BYTES;
+constexpr uint32_t OFF_H1 = OFF_W2 + W2_BYTES;
+constexpr uint32_t OFF_H2 = OFF_H1 + H1_BYTES;
+constexpr uint32_t OFF_X = OFF_H2 + H2_BYTES;            // float xs[4][PT]
+constexpr uint32_t OFF_W1 = OFF_X + 4 * PT * 4;          // float4 w1[64] + float b1[64]
+constexpr uint32_t OFF_MAX = OFF_W1 + 64 * 16 + 64 * 4;  // float mx[2][128] (warps 4-7 -> warps 0-3)
+constexpr uint32_t SMEM_TOTAL = OFF_MAX + 2 * 128 * 4;
+
+struct TcTrunkParams {
+  const float* x;        // [B,C,P]
+  const float* trans;    // [B,9] or nullptr (STN trunk)
+  const float* w1;       // [64,C] folded fp32
+  const float* b1;       // [64]
+  const uint8_t* w2img;  // FP16 operand image of layer 2 (W2_BYTES)
+  const uint8_t* w3img;  // FP16 operand images of layer 3: 4 quarters x W3Q_BYTES
+  float* maxbuf;         // [B,1024] raw maxima (bias / ReLU applied by decode_kernel)
+  int B, C, P;
+};
+
+// folded fp32 weights -> FP16 UMMA operand images (runs per forward; ~300 KB)
+__global__ void pointnet_pack_kernel(const float* __restrict__ w2, const float* __restrict__ b2,
+                                     const float* __restrict__ w3, uint8_t* __restrict__ w2img, uint8_t* __restrict__ w3img) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = gid; i < 128 * K1; i += stride) {          // W2 image: row = channel, K = 64 + fold
+    const int c = i / K1, k = i - c * K1;
+    float v = 0.f;
+    if (k < 64) v = w2[c * 64 + k];
+    else if (k == 64) v = b2[c];                           // multiplied by the 1.0 column of h1
+    *reinterpret_cast<__half*>(w2img + (size_t)(k >> 3) * 128 * 16 + (size_t)c * 16 + (k & 7) * 2) = __float2half_rn(v);
+  }
+  for (int i = gid; i < 1024 * 128; i += stride) {        // W3 images: 4 quarters of 256 channels
+    const int c = i >> 7, k = i & 127;
+    const int q = c >> 8, r = c & 255;
+    *reinterpret_cast<__half*>(w3img + (size_t)q * W3Q_BYTES + (size_t)(k >> 3) * 256 * 16 + (size_t)r * 16 + (k & 7) * 2) =
+        __float2half_rn(w3[i]);
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {   // {relu(lo), relu(hi)} as fp16 pair
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+template <bool MAIN>
+__global__ void __launch_bounds__(NT, 1) pointnet_trunk_tc_kernel(const TcTrunkParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int serr;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = blockIdx.x & 3;                       // channel quarter
+  const int group = blockIdx.x >> 2, ngroups = gridDim.x >> 2;
+  const int C = p.C, P = p.P;
+  float* xs = reinterpret_cast<float*>(smem + OFF_X);
+  float4* w1s = reinterpret_cast<float4*>(smem + OFF_W1);
+  float* b1s = reinterpret_cast<float*>(smem + OFF_W1 + 64 * 16);
+  float* mxs = reinterpret_cast<float*>(smem + OFF_MAX);
+
+  // ---- one-time setup: weights of this CTA into shared memory, TMEM, barrier ---------------------
+  {
+    const uint4* src3 = reinterpret_cast<const uint4*>(p.w3img + (size_t)q * W3Q_BYTES);
+    uint4* dst3 = reinterpret_cast<uint4*>(smem + OFF_W3Q);
+    for (uint32_t i = tid; i < W3Q_BYTES / 16; i += NT) dst3[i] = __ldg(src3 + i);
+    const uint4* src2 = reinterpret_cast<const uint4*>(p.w2img);
+    uint4* dst2 = reinterpret_cast<uint4*>(smem + OFF_W2);
+    for (uint32_t i = tid; i < W2_BYTES / 16; i += NT) dst2[i] = __ldg(src2 + i);
+    if (tid < 64) {
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      w.x = __ldg(p.w1 + tid * C + 0); w.y = __ldg(p.w1 + tid * C + 1); w.z = __ldg(p.w1 + tid * C + 2);
+      if (C > 3) w.w = __ldg(p.w1 + tid * C + 3);
+      w1s[tid] = w;
+      b1s[tid] = __ldg(p.b1 + tid);
+    }
+    // fold k-chunks of the h1 image (columns 64..79): column 64 = 1.0 for every point, rest 0 — constant
+    for (int r = tid; r < PT; r += NT) {
+      uint4 one = make_uint4(0x00003c00u, 0u, 0u, 0u);   // fp16 1.0 in element 0
+      *reinterpret_cast<uint4*>(smem + OFF_H1 + 8 * PT * 16 + r * 16) = one;
+      *reinterpret_cast<uint4*>(smem + OFF_H1 + 9 * PT * 16 + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  if (tid == 0) {
+    serr = 0;
+    tc::mbar_init(&bar_mma, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  volatile int* errw = &serr;
+  uint32_t mma_phase = 0;
+
+  const uint32_t idesc = tc::make_idesc_f16(128, 128, 0);
+  const uint64_t d_h1 = tc::make_smem_desc(tc::smem_u32(smem + OFF_H1), PT * 16, 128);
+  const uint64_t d_w2 = tc::make_smem_desc(tc::smem_u32(smem + OFF_W2), 128 * 16, 128);
+  const uint64_t d_w3 = tc::make_smem_desc(tc::smem_u32(smem + OFF_W3Q), 256 * 16, 128);
+  const uint64_t d_h2 = tc::make_smem_desc(tc::smem_u32(smem + OFF_H2), PT * 16, 128);
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const int ntiles = (P + PT - 1) / PT;
+
+  for (int b = group; b < p.B; b += ngroups) {
+    float run0 = -INFINITY, run1 = -INFINITY;   // running max of channels (q*256 + mc*128 + (warp&3)*32 + lane), mc = 0,1
+    float t00 = 1.f, t01 = 0.f, t02 = 0.f, t10 = 0.f, t11 = 1.f, t12 = 0.f, t20 = 0.f, t21 = 0.f, t22 = 1.f;
+    if (MAIN) {
+      const float* t = p.trans + (size_t)b * 9;
+      t00 = __ldg(t + 0); t01 = __ldg(t + 1); t02 = __ldg(t + 2); t10 = __ldg(t + 3); t11 = __ldg(t + 4);
+      t12 = __ldg(t + 5); t20 = __ldg(t + 6); t21 = __ldg(t + 7); t22 = __ldg(t + 8);
+    }
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int p0 = tile * PT;
+      const int npts = min(PT, P - p0);
+      // ---- L1: thread = point; points past the end replicate the last valid one -----------------
+      {
+        const int pp = p0 + min(tid, npts - 1);
+        const float* xb = p.x + (size_t)b * C * P + pp;
+        float x0 = __ldg(xb), x1 = __ldg(xb + P), x2 = __ldg(xb + 2 * (size_t)P);
+        const float x3 = C > 3 ? __ldg(xb + 3 * (size_t)P) : 0.f;
+        if (MAIN) {   // bmm([P,3],[3,3]) (:146): out_j = sum_i x_i T[i][j], sequential-i fmaf
+          const float y0 = fmaf(x2, t20, fmaf(x1, t10, x0 * t00));
+          const float y1 = fmaf(x2, t21, fmaf(x1, t11, x0 * t01));
+          const float y2 = fmaf(x2, t22, fmaf(x1, t12, x0 * t02));
+          x0 = y0; x1 = y1; x2 = y2;
+        }
+        uint8_t* row = smem + OFF_H1 + tid * 16;
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c0 = kc * 8 + e * 2;
+            const float4 wa = w1s[c0], wb = w1s[c0 + 1];
+            const float va = fmaf(wa.w, x3, fmaf(wa.z, x2, fmaf(wa.y, x1, wa.x * x0))) + b1s[c0];
+            const float vb = fmaf(wb.w, x3, fmaf(wb.z, x2, fmaf(wb.y, x1, wb.x * x0))) + b1s[c0 + 1];
+            pk[e] = pack_relu_f16x2(va, vb);
+          }
+          *reinterpret_cast<uint4*>(row + kc * PT * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      tc::fence_proxy_async_smem();
+      __syncthreads();
+      // ---- L2: two M=128 halves of points, N = 128 channels, K = 80 ------------------------------
+      if (tid == 0) {
+        tc::tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint64_t ad = d_h1 + (uint64_t)((h * 128 * 16) >> 4), bd = d_w2;
+#pragma unroll
+          for (int j = 0; j < K1 / 16; ++j) {
+            tc::umma_f16(tmem + (uint32_t)h * 128u, ad, bd, idesc, j > 0 ? 1u : 0u);
+            ad += (uint64_t)((2 * PT * 16) >> 4); bd += (uint64_t)((2 * 128 * 16) >> 4);
+          }
+        }
+        tc::umma_commit(&bar_mma);
+      }
+      if (!tc::mbar_wait(&bar_mma, mma_phase, errw, 1)) break;
+      mma_phase ^= 1u;
+      tc::tc_fence_after();
+      // L2 epilogue: thread = point (warp w: half = w / 4, TMEM lane quarter = w % 4)
+      {
+        const int half = warp >> 2;
+        const int prow = half * 128 + (warp & 3) * 32 + lane;
+        uint8_t* row = smem + OFF_H2 + prow * 16;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tc::tmem_ld32(tmem + lane_addr + (uint32_t)half * 128u + (uint32_t)c0, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              pk[e] = pack_relu_f16x2(__uint_as_float(v[kc * 8 + e * 2]), __uint_as_float(v[kc * 8 + e * 2 + 1]));
+            *reinterpret_cast<uint4*>(row + (c0 / 8 + kc) * PT * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async_smem();
+      __syncthreads();
+      // ---- L3: per 128-channel chunk, both point halves (two 128-column accumulators) -------------
+#pragma unroll 1
+      for (int mc = 0; mc < 2; ++mc) {
+        if (tid == 0) {
+          tc::tc_fence_after();
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            uint64_t ad = d_w3 + (uint64_t)((mc * 128 * 16) >> 4), bd = d_h2 + (uint64_t)((ph * 128 * 16) >> 4);
+#pragma unroll
+            for (int j = 0; j < 128 / 16; ++j) {
+              tc::umma_f16(tmem + 256u + (uint32_t)ph * 128u, ad, bd, idesc, j > 0 ? 1u : 0u);
+              ad += (uint64_t)((2 * 256 * 16) >> 4); bd += (uint64_t)((2 * PT * 16) >> 4);
+            }
+          }
+          tc::umma_commit(&bar_mma);
+        }
+        if (!tc::mbar_wait(&bar_mma, mma_phase, errw, 2)) break;
+        mma_phase ^= 1u;
+        tc::tc_fence_after();
+        // epilogue: lane = channel, columns = points: thread-local 3-input max (warps 4-7 take point half 1)
+        float m = -INFINITY;
+        const int ph = warp >> 2;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tc::tmem_ld32(tmem + lane_addr + 256u + (uint32_t)ph * 128u + (uint32_t)c0, v);
+          tc::tmem_ld_wait();
+          float a[11];
+#pragma unroll
+          for (int i = 0; i < 10; ++i) a[i] = max3f(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+          a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+          m = max3f(m, max3f(a[0], a[1], a[2]), max3f(a[3], a[4], a[5]));
+          m = max3f(m, max3f(a[6], a[7], a[8]), fmaxf(a[9], a[10]));
+        }
+        if (mc == 0) run0 = fmaxf(run0, m); else run1 = fmaxf(run1, m);
+        tc::tc_fence_before();
+        __syncthreads();   // accumulators drained before the next chunk's MMAs overwrite them
+      }
+      if (*errw) break;
+    }
+    // ---- cloud done: combine the two point-half partials and write this quarter's 256 maxima ------
+    if (warp >= 4) { mxs[(warp & 3) * 32 + lane] = run0; mxs[128 + (warp & 3) * 32 + lane] = run1; }
+    __syncthreads();
+    if (warp < 4) {
+      const int c = warp * 32 + lane;
+      float* out = p.maxbuf + (size_t)b * 1024 + q * 256;
+      out[c] = fmaxf(run0, mxs[c]);
+      out[128 + c] = fmaxf(run1, mxs[128 + c]);
+    }
+    __syncthreads();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+size_t pointnet_tc_image_bytes() { return align_up((size_t)W2_BYTES, 256) + 4 * (size_t)W3Q_BYTES; }
+
+int launch_pointnet_tc_trunk(const float* x, const float* trans, const float* w1, const float* b1, const float* w2,
+                             const float* b2, const float* w3, int B, int C, int P, float* maxbuf, void* images,
+                             bool main_trunk, cudaStream_t s) {
+  DeviceProps dp;
+  int rc = device_props(&dp);
+  if (rc) return rc;
+  uint8_t* w2img = static_cast<uint8_t*>(images);
+  uint8_t* w3img = w2img + align_up((size_t)W2_BYTES, 256);
+  pointnet_pack_kernel<<<64, 256, 0, s>>>(w2, b2, w3, w2img, w3img);
+  DVQ_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  TcTrunkParams p;
+  p.x = x; p.trans = trans; p.w1 = w1; p.b1 = b1; p.w2img = w2img; p.w3img = w3img; p.maxbuf = maxbuf; p.B = B; p.C = C; p.P = P;
+  int groups = (dp.sm_count + 3) / 4;
+  if (groups > B) groups = B;
+  const size_t smem = SMEM_TOTAL + 128;
+  if (main_trunk) {
+    DVQ_CUDA_CHECK(cudaFuncSetAttribute(pointnet_trunk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pointnet_trunk_tc_kernel<true><<<groups * 4, NT, smem, s>>>(p);
+  } else {
+    DVQ_CUDA_CHECK(cudaFuncSetAttribute(pointnet_trunk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pointnet_trunk_tc_kernel<false><<<groups * 4, NT, smem, s>>>(p);
+  }
+  DVQ_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return DVQ_OK;
+}
+
+}  // namespace dvq

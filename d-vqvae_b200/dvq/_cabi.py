@@ -44,6 +44,8 @@ SYMBOLS = {
     "dvq_vq_forward_host": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, C.POINTER(_f), C.POINTER(_f)]),
     "dvq_pointnet_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "dvq_pointnet_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "dvq_pointnet_workspace_bytes_ex": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
+    "dvq_pointnet_forward_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "dvq_allreduce_stats": (_i, [_vp, _vp, _vp, _i, _vp]),
 }
 
@@ -94,9 +96,12 @@ def vq_workspace_bytes(n: int, k: int, d: int, flags: int) -> int:
     return out.value
 
 
-def pointnet_workspace_bytes(b: int, c: int, p: int) -> int:
+DVQ_PN_FP16_TC = 0x1
+
+
+def pointnet_workspace_bytes(b: int, c: int, p: int, flags: int = 0) -> int:
     out = C.c_size_t()
-    check(lib.dvq_pointnet_workspace_bytes(b, c, p, C.byref(out)), "dvq_pointnet_workspace_bytes")
+    check(lib.dvq_pointnet_workspace_bytes_ex(b, c, p, flags, C.byref(out)), "dvq_pointnet_workspace_bytes_ex")
     return out.value
 
 

@@ -72,6 +72,9 @@ class PointNetEncoder(nn.Module):
         self.global_feat = global_feat
         self.feature_transform = feature_transform
         self.channel = channel
+        # "fp32": all-FP32 CUDA-core kernel (parity 5e-5 vs the CPU reference); "fp16_tc": layers 2-3 on
+        # tcgen05 tensor cores, FP16 operands / FP32 accumulation (3e-3; what TF32 cuDNN gives the reference)
+        self.precision = "fp32"
         self._folded = None
         self._folded_key = None
         self._ws = None
@@ -125,12 +128,15 @@ class PointNetEncoder(nn.Module):
         blob, st = self.folded_weights()
         feat = torch.empty((B, 1024), dtype=torch.float32, device=x.device)
         trans = torch.empty((B, 3, 3), dtype=torch.float32, device=x.device)
-        need = _cabi.pointnet_workspace_bytes(B, Cc, P)
+        if self.precision not in ("fp32", "fp16_tc"):
+            raise ValueError("precision must be 'fp32' or 'fp16_tc'")
+        flags = _cabi.DVQ_PN_FP16_TC if self.precision == "fp16_tc" else 0
+        need = _cabi.pointnet_workspace_bytes(B, Cc, P, flags)
         if self._ws is None or self._ws.device != x.device or self._ws.numel() < need:
             self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
-            _cabi.check(_cabi.lib.dvq_pointnet_forward(
-                x.data_ptr(), C.addressof(st), B, Cc, P, feat.data_ptr(), trans.data_ptr(),
+            _cabi.check(_cabi.lib.dvq_pointnet_forward_ex(
+                x.data_ptr(), C.addressof(st), B, Cc, P, flags, feat.data_ptr(), trans.data_ptr(),
                 self._ws.data_ptr(), self._ws.numel(), torch.cuda.current_stream(x.device).cuda_stream),
-                "dvq_pointnet_forward")
+                "dvq_pointnet_forward_ex")
         return feat, trans, None

@@ -136,6 +136,13 @@ typedef struct DvqPointNetWeights {
   const float *w3, *b3;               /* [1024,128] conv3+bn3 (no ReLU)      :162 */
 } DvqPointNetWeights;
 DVQ_API int dvq_pointnet_workspace_bytes(int B, int C, int P, size_t* bytes);
+/* Same forward with a precision choice.  flags = 0: all-FP32 CUDA-core kernel (parity reference, 5e-5);
+ * DVQ_PN_FP16_TC: the 64->128 and 128->1024 layers on tcgen05 tensor cores with FP16 operands and FP32
+ * accumulation (10-bit mantissa, as the TF32 cuDNN convolutions the reference runs on a GPU; 3e-3). */
+#define DVQ_PN_FP16_TC 0x1
+DVQ_API int dvq_pointnet_workspace_bytes_ex(int B, int C, int P, int flags, size_t* bytes);
+DVQ_API int dvq_pointnet_forward_ex(const float* x, const DvqPointNetWeights* w, int B, int C, int P, int flags,
+                                    float* feat, float* trans, void* workspace, size_t workspace_bytes, void* stream);
 DVQ_API int dvq_pointnet_forward(const float* x, const DvqPointNetWeights* w, int B, int C, int P,
                          float* feat, float* trans, void* workspace, size_t workspace_bytes, void* stream);
 

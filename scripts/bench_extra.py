@@ -37,6 +37,15 @@ for B in (64, 512, 4096):
             fo, to_, _ = net(x)
         rec.update({"torch_ops_ms": ms_t, "speedup_vs_torch_ops": ms_t / ms,
                     "max_abs_diff_vs_torch_ops_tf32": float((fo - ft).abs().max()), "feat_scale": float(ft.abs().max())})
+    net.precision = "fp16_tc"
+    ms_tc = timeit(lambda: net(x), iters=5)
+    with torch.no_grad():
+        f_tc, _, _ = net(x)
+    net.precision = "fp32"
+    with torch.no_grad():
+        f_32, _, _ = net(x)
+    rec.update({"fp16_tc_ms": ms_tc, "fp16_tc_clouds_per_s": B / ms_tc * 1e3, "fp16_tc_tflops": flop / ms_tc / 1e9,
+                "fp16_tc_max_abs_diff_vs_fp32_kernel": float((f_tc - f_32).abs().max()), "feat_scale_fp32": float(f_32.abs().max())})
     out["pointnet_B%d_P3000_C4" % B] = rec
     print("pointnet", B, rec, flush=True)
 

@@ -78,3 +78,34 @@ def test_pointnet_refuses_training_mode_and_bad_shapes():
         net.conv3.weight.mul_(2.0)
     f1, _, _ = net(torch.ones(1, 4, 5, device="cuda"))
     assert not torch.equal(f0, f1)
+
+
+TOL_TC = 3e-3   # FP16 operands (10-bit mantissa, = the TF32 cuDNN path of the reference on a GPU), FP32 accumulation
+
+
+@pytest.mark.parametrize("name", PN_CASES)
+def test_pointnet_fp16_tc_matches_reference_golden(name):
+    g = load_gold(name)
+    b, c, p, seed = [int(v) for v in g["meta"]]
+    net = _encoder(seed, c)
+    net.precision = "fp16_tc"
+    x = torch.from_numpy(po.make_cloud(seed + 1, b, c, p)).cuda()
+    feat, trans, tf = net(x)
+    assert tf is None and tuple(feat.shape) == (b, 1024)
+    scale = float(np.abs(g["feat"]).max())
+    assert np.abs(feat.cpu().numpy() - g["feat"]).max() <= TOL_TC * scale
+    assert np.abs(trans.cpu().numpy() - g["trans"]).max() <= TOL_TC * max(1.0, float(np.abs(g["trans"]).max()))
+
+
+def test_pointnet_fp16_tc_vs_fp32_kernel_many_clouds():
+    """More clouds than CTAs-groups, ragged point count: the persistent cloud loop and the tail tile."""
+    net = _encoder(31, 4)
+    x = torch.from_numpy(po.make_cloud(32, 70, 4, 1037)).cuda()
+    f32, t32, _ = net(x)
+    net.precision = "fp16_tc"
+    f16, t16, _ = net(x)
+    scale = float(f32.abs().max())
+    assert float((f16 - f32).abs().max()) <= TOL_TC * scale
+    assert float((t16 - t32).abs().max()) <= TOL_TC * max(1.0, float(t32.abs().max()))
+    f16b, _, _ = net(x[5:6].contiguous())
+    assert torch.equal(f16b, f16[5:6])                     # clouds are independent, result is deterministic
