@@ -21,8 +21,8 @@
 // 256 KB of layer-3 weights per tile from L2.
 //
 // Roofline: tensor pipe; algorithmic 2 * 139 520 flop per point per trunk, 16 * P bytes in + 4 KB out
-// per cloud.  Phases inside a CTA are serialised by __syncthreads in this version (L1 / L2 / L3 do not
-// overlap yet), see DESIGN.md.
+// per cloud.  Inside a CTA the CUDA-core layer 1 of tile t+1 runs under the layer-3 MMAs of tile t; the
+// layer-2 MMA + epilogue and the layer-3 epilogues are still exposed (one CTA per SM), see DESIGN.md.
 #include <cuda_fp16.h>
 
 #include "dvq_common.cuh"
@@ -32,7 +32,8 @@ namespace dvq {
 namespace {
 
 constexpr int PT = 256;                 // points per tile
-constexpr int NT = 256;                 // threads per CTA (thread <-> point in L1 / L2 epilogue)
+constexpr int NC = 256;                 // compute threads (thread <-> point in L1 / L2 epilogue)
+constexpr int NT = NC + 32;             // + one warp whose lane 0 only issues the MMAs (keeps the compute warps free)
 constexpr int K1 = 80;                  // layer-2 contraction length: 64 channels + 16 fold columns
 constexpr int KC1 = K1 / 8;             // 8-wide k-chunks of the layer-2 operands
 constexpr int KC2 = 128 / 8;            // k-chunks of the layer-3 operands
@@ -96,10 +97,12 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
 template <bool MAIN>
 __global__ void __launch_bounds__(NT, 1) pointnet_trunk_tc_kernel(const TcTrunkParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_mma;
+  __shared__ uint64_t bar_l2, bar_l3[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int serr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool compute = warp < NC / 32;                // warps 0-7; warp 8 issues the tensor-core work
+  const bool issuer = (tid == NC);
   const int q = blockIdx.x & 3;                       // channel quarter
   const int group = blockIdx.x >> 2, ngroups = gridDim.x >> 2;
   const int C = p.C, P = p.P;
@@ -132,7 +135,9 @@ __global__ void __launch_bounds__(NT, 1) pointnet_trunk_tc_kernel(const TcTrunkP
   }
   if (tid == 0) {
     serr = 0;
-    tc::mbar_init(&bar_mma, 1);
+    tc::mbar_init(&bar_l2, 1);
+    tc::mbar_init(&bar_l3[0], 1);
+    tc::mbar_init(&bar_l3[1], 1);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(NT, 1) pointnet_trunk_tc_kernel(const TcTrunkP
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
   volatile int* errw = &serr;
-  uint32_t mma_phase = 0;
+  uint32_t phase = 0;   // every barrier completes exactly once per tile
 
   const uint32_t idesc = tc::make_idesc_f16(128, 128, 0);
   const uint64_t d_h1 = tc::make_smem_desc(tc::smem_u32(smem + OFF_H1), PT * 16, 128);
@@ -160,40 +165,60 @@ __global__ void __launch_bounds__(NT, 1) pointnet_trunk_tc_kernel(const TcTrunkP
       t00 = __ldg(t + 0); t01 = __ldg(t + 1); t02 = __ldg(t + 2); t10 = __ldg(t + 3); t11 = __ldg(t + 4);
       t12 = __ldg(t + 5); t20 = __ldg(t + 6); t21 = __ldg(t + 7); t22 = __ldg(t + 8);
     }
-    for (int tile = 0; tile < ntiles; ++tile) {
+    // L1 of one tile: thread = point; points past the end replicate the last valid one
+    auto layer1 = [&](int tile) {
       const int p0 = tile * PT;
       const int npts = min(PT, P - p0);
-      // ---- L1: thread = point; points past the end replicate the last valid one -----------------
-      {
-        const int pp = p0 + min(tid, npts - 1);
-        const float* xb = p.x + (size_t)b * C * P + pp;
-        float x0 = __ldg(xb), x1 = __ldg(xb + P), x2 = __ldg(xb + 2 * (size_t)P);
-        const float x3 = C > 3 ? __ldg(xb + 3 * (size_t)P) : 0.f;
-        if (MAIN) {   // bmm([P,3],[3,3]) (:146): out_j = sum_i x_i T[i][j], sequential-i fmaf
-          const float y0 = fmaf(x2, t20, fmaf(x1, t10, x0 * t00));
-          const float y1 = fmaf(x2, t21, fmaf(x1, t11, x0 * t01));
-          const float y2 = fmaf(x2, t22, fmaf(x1, t12, x0 * t02));
-          x0 = y0; x1 = y1; x2 = y2;
-        }
-        uint8_t* row = smem + OFF_H1 + tid * 16;
+      const int pp = p0 + min(tid, npts - 1);
+      const float* xb = p.x + (size_t)b * C * P + pp;
+      float x0 = __ldg(xb), x1 = __ldg(xb + P), x2 = __ldg(xb + 2 * (size_t)P);
+      const float x3 = C > 3 ? __ldg(xb + 3 * (size_t)P) : 0.f;
+      if (MAIN) {   // bmm([P,3],[3,3]) (:146): out_j = sum_i x_i T[i][j], sequential-i fmaf
+        const float y0 = fmaf(x2, t20, fmaf(x1, t10, x0 * t00));
+        const float y1 = fmaf(x2, t21, fmaf(x1, t11, x0 * t01));
+        const float y2 = fmaf(x2, t22, fmaf(x1, t12, x0 * t02));
+        x0 = y0; x1 = y1; x2 = y2;
+      }
+      uint8_t* row = smem + OFF_H1 + tid * 16;
 #pragma unroll
-        for (int kc = 0; kc < 8; ++kc) {
-          uint32_t pk[4];
+      for (int kc = 0; kc < 8; ++kc) {
+        uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c0 = kc * 8 + e * 2;
-            const float4 wa = w1s[c0], wb = w1s[c0 + 1];
-            const float va = fmaf(wa.w, x3, fmaf(wa.z, x2, fmaf(wa.y, x1, wa.x * x0))) + b1s[c0];
-            const float vb = fmaf(wb.w, x3, fmaf(wb.z, x2, fmaf(wb.y, x1, wb.x * x0))) + b1s[c0 + 1];
-            pk[e] = pack_relu_f16x2(va, vb);
-          }
-          *reinterpret_cast<uint4*>(row + kc * PT * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int e = 0; e < 4; ++e) {
+          const int c0 = kc * 8 + e * 2;
+          const float4 wa = w1s[c0], wb = w1s[c0 + 1];
+          const float va = fmaf(wa.w, x3, fmaf(wa.z, x2, fmaf(wa.y, x1, wa.x * x0))) + b1s[c0];
+          const float vb = fmaf(wb.w, x3, fmaf(wb.z, x2, fmaf(wb.y, x1, wb.x * x0))) + b1s[c0 + 1];
+          pk[e] = pack_relu_f16x2(va, vb);
         }
+        *reinterpret_cast<uint4*>(row + kc * PT * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       tc::fence_proxy_async_smem();
-      __syncthreads();
-      // ---- L2: two M=128 halves of points, N = 128 channels, K = 80 ------------------------------
-      if (tid == 0) {
+    };
+    // L3 epilogue of one 128-channel chunk: lane = channel, columns = points, thread-local 3-input max
+    auto chunk_max = [&](uint32_t col_base) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem + lane_addr + col_base + (uint32_t)(warp >> 2) * 128u + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
+        float a[11];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) a[i] = max3f(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+        a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+        m = max3f(m, max3f(a[0], a[1], a[2]), max3f(a[3], a[4], a[5]));
+        m = max3f(m, max3f(a[6], a[7], a[8]), fmaxf(a[9], a[10]));
+      }
+      return m;
+    };
+
+    if (compute) layer1(0);
+    __syncthreads();
+    bool ok = true;
+    for (int tile = 0; ok && tile < ntiles; ++tile) {
+      // ---- L2: two M=128 halves of points, N = 128 channels, K = 80 -> TMEM columns [0,256) ----------
+      if (issuer) {
         tc::tc_fence_after();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -204,13 +229,12 @@ __global__ void __launch_bounds__(NT, 1) pointnet_trunk_tc_kernel(const TcTrunkP
             ad += (uint64_t)((2 * PT * 16) >> 4); bd += (uint64_t)((2 * 128 * 16) >> 4);
           }
         }
-        tc::umma_commit(&bar_mma);
+        tc::umma_commit(&bar_l2);
       }
-      if (!tc::mbar_wait(&bar_mma, mma_phase, errw, 1)) break;
-      mma_phase ^= 1u;
+      if (!tc::mbar_wait(&bar_l2, phase, errw, 1)) { ok = false; break; }
       tc::tc_fence_after();
       // L2 epilogue: thread = point (warp w: half = w / 4, TMEM lane quarter = w % 4)
-      {
+      if (compute) {
         const int half = warp >> 2;
         const int prow = half * 128 + (warp & 3) * 32 + lane;
         uint8_t* row = smem + OFF_H2 + prow * 16;
@@ -232,48 +256,38 @@ __global__ void __launch_bounds__(NT, 1) pointnet_trunk_tc_kernel(const TcTrunkP
       tc::tc_fence_before();
       tc::fence_proxy_async_smem();
       __syncthreads();
-      // ---- L3: per 128-channel chunk, both point halves (two 128-column accumulators) -------------
-#pragma unroll 1
-      for (int mc = 0; mc < 2; ++mc) {
-        if (tid == 0) {
-          tc::tc_fence_after();
+      // ---- L3: both 128-channel chunks issued back to back (chunk 0 -> columns [256,512), chunk 1 ->
+      //      the columns [0,256) the L2 epilogue just drained); the CUDA-core layer 1 of the NEXT tile
+      //      runs underneath these 2048 tensor-pipe cycles ---------------------------------------------
+      if (issuer) {
+        tc::tc_fence_after();
+#pragma unroll
+        for (int mc = 0; mc < 2; ++mc) {
 #pragma unroll
           for (int ph = 0; ph < 2; ++ph) {
             uint64_t ad = d_w3 + (uint64_t)((mc * 128 * 16) >> 4), bd = d_h2 + (uint64_t)((ph * 128 * 16) >> 4);
 #pragma unroll
             for (int j = 0; j < 128 / 16; ++j) {
-              tc::umma_f16(tmem + 256u + (uint32_t)ph * 128u, ad, bd, idesc, j > 0 ? 1u : 0u);
+              tc::umma_f16(tmem + (mc == 0 ? 256u : 0u) + (uint32_t)ph * 128u, ad, bd, idesc, j > 0 ? 1u : 0u);
               ad += (uint64_t)((2 * 256 * 16) >> 4); bd += (uint64_t)((2 * PT * 16) >> 4);
             }
           }
-          tc::umma_commit(&bar_mma);
+          tc::umma_commit(&bar_l3[mc]);
         }
-        if (!tc::mbar_wait(&bar_mma, mma_phase, errw, 2)) break;
-        mma_phase ^= 1u;
-        tc::tc_fence_after();
-        // epilogue: lane = channel, columns = points: thread-local 3-input max (warps 4-7 take point half 1)
-        float m = -INFINITY;
-        const int ph = warp >> 2;
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tc::tmem_ld32(tmem + lane_addr + 256u + (uint32_t)ph * 128u + (uint32_t)c0, v);
-          tc::tmem_ld_wait();
-          float a[11];
-#pragma unroll
-          for (int i = 0; i < 10; ++i) a[i] = max3f(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
-          a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-          m = max3f(m, max3f(a[0], a[1], a[2]), max3f(a[3], a[4], a[5]));
-          m = max3f(m, max3f(a[6], a[7], a[8]), fmaxf(a[9], a[10]));
-        }
-        if (mc == 0) run0 = fmaxf(run0, m); else run1 = fmaxf(run1, m);
-        tc::tc_fence_before();
-        __syncthreads();   // accumulators drained before the next chunk's MMAs overwrite them
       }
-      if (*errw) break;
+      if (compute && tile + 1 < ntiles) layer1(tile + 1);   // h1 is free: the L2 MMAs of this tile completed above
+      if (!tc::mbar_wait(&bar_l3[0], phase, errw, 2)) { ok = false; break; }
+      tc::tc_fence_after();
+      if (compute) run0 = fmaxf(run0, chunk_max(256u));
+      if (!tc::mbar_wait(&bar_l3[1], phase, errw, 3)) { ok = false; break; }
+      tc::tc_fence_after();
+      if (compute) run1 = fmaxf(run1, chunk_max(0u));
+      phase ^= 1u;
+      tc::tc_fence_before();
+      __syncthreads();   // accumulators drained, h1(tile+1) complete, h2 free for the next L2 epilogue
     }
     // ---- cloud done: combine the two point-half partials and write this quarter's 256 maxima ------
-    if (warp >= 4) { mxs[(warp & 3) * 32 + lane] = run0; mxs[128 + (warp & 3) * 32 + lane] = run1; }
+    if (compute && warp >= 4) { mxs[(warp & 3) * 32 + lane] = run0; mxs[128 + (warp & 3) * 32 + lane] = run1; }
     __syncthreads();
     if (warp < 4) {
       const int c = warp * 32 + lane;
