@@ -12,7 +12,8 @@
 //     B row  = [ eh (D) |          fold (16) ]     eh = fp16(-2 e')
 // issued as zh.eh + zl.eh + fold.fold; the fold columns carry g_n*B_n and g_n*ee_k as products of
 // FP16 pairs (ee_k split in three FP16 terms).  Because acc >= 0 its bit pattern is monotone, so the
-// epilogue packs the 5-bit local column index into the low mantissa bits and takes FMNMX3 minima.
+// epilogue reduces raw accumulators with 3-input FMNMX3 minima and recovers the winning column from the
+// indicator bit masks of its ambiguity count (no per-element index packing).
 //
 // Rigor.  eps_n bounds |acc - exact| for every k of row n (operand rounding: |z'| * max_k||eh_k+2e'_k||
 // measured exactly by the prep kernel; FP16 lo-term rounding; tensor-core FP32 accumulation;
@@ -254,19 +255,40 @@ __device__ __forceinline__ float half_minus_float(uint32_t h16, float a) {
 }
 
 struct RowState {   // per (row, column subset) running result of the filter
-  float m1;         // smallest key so far (index in the 5 low bits)
-  float cnt;        // number of OTHER keys within `band` of m1 (a superset count)
-  int col;          // global code index of m1
+  float m1;         // smallest accumulator value so far
+  int cnt;          // number of OTHER keys within `band` of m1 (a superset count)
+  int col;          // global code index of m1 (meaningful when the row is decided: cnt == 0)
   uint32_t cand;    // groups of sub-chunks holding a key within `band` of m1 (superset; always holds m1's own)
 };
 
-// One 32-column sub-chunk: keys -> FMNMX3 tree -> running minimum with exact reset -> count of keys
-// inside the band on the FMA pipe (fma.sat((T - key) * BIG) is exactly 0 or 1).
-__device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], uint32_t mask, int col0, uint32_t gbit, float band, RowState& st) {
+// packed f32x2 helpers (Blackwell FFMA2: two FP32 FMAs per issued instruction)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// One 32-column sub-chunk of raw accumulators (all >= 0, so float order == bit order):
+//   pass 1  FMNMX3 tree -> sub-chunk minimum -> running minimum with exact reset of the ambiguity state;
+//   pass 2  indicator of "key < m1 + band" per element, fma.sat((T - key) * BIG) in {0, 1} exactly, shifted
+//           into two 16-bit masks (even / odd columns) by a packed Horner step acc2 = 2 * acc2 + {s0, s1}
+//           (one FFMA2 per two elements).  popc of the masks is the count; the position of the set bit is
+//           the column of the minimum for a decided row (after the last reset the only key that was ever
+//           inside the band is the minimum itself), so no per-element index packing is needed.
+// ~3 issued instructions per element: 0.5 FMNMX3 (ALU) + 1 FFMA.SAT + 0.5 FFMA2 (FMA pipe).
+__device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uint32_t gbit, float band, RowState& st) {
   const float BIG = 1048576.f;
   float key[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(pack_key(v[j], mask, (uint32_t)j));
+  for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(v[j]);
   float a0 = min3f(key[0], key[1], key[2]), a1 = min3f(key[3], key[4], key[5]);
   float a2 = min3f(key[6], key[7], key[8]), a3 = min3f(key[9], key[10], key[11]);
   float a4 = min3f(key[12], key[13], key[14]), a5 = min3f(key[15], key[16], key[17]);
@@ -278,22 +300,32 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], uint32_t mask
   // minimum's own hit below); a smaller improvement leaves the old minimum inside the band, which the
   // new minimum's own hit accounts for.
   if (m < st.m1) {
-    if (st.m1 - m > band) { st.cnt = -1.f; st.cand = 0u; }
+    if (st.m1 - m > band) { st.cnt = -1; st.cand = 0u; }
     st.m1 = m;
-    st.col = col0 + (int)(__float_as_uint(m) & 31u);
   }
   const float TB = (st.m1 + band) * BIG;
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+  const uint64_t two = pack_f32x2(2.f, 2.f);
+  // four independent Horner chains of 4 steps (columns 0-7, 8-15, 16-23, 24-31): short dependency chains
+  uint64_t h0 = pack_f32x2(0.f, 0.f), h1 = h0, h2 = h0, h3 = h0;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    c0 += fma_sat(key[j + 0], -BIG, TB);
-    c1 += fma_sat(key[j + 1], -BIG, TB);
-    c2 += fma_sat(key[j + 2], -BIG, TB);
-    c3 += fma_sat(key[j + 3], -BIG, TB);
+  for (int j = 0; j < 8; j += 2) {
+    h0 = ffma2(h0, two, pack_f32x2(fma_sat(key[j], -BIG, TB), fma_sat(key[j + 1], -BIG, TB)));
+    h1 = ffma2(h1, two, pack_f32x2(fma_sat(key[8 + j], -BIG, TB), fma_sat(key[9 + j], -BIG, TB)));
+    h2 = ffma2(h2, two, pack_f32x2(fma_sat(key[16 + j], -BIG, TB), fma_sat(key[17 + j], -BIG, TB)));
+    h3 = ffma2(h3, two, pack_f32x2(fma_sat(key[24 + j], -BIG, TB), fma_sat(key[25 + j], -BIG, TB)));
   }
-  const float csub = (c0 + c1) + (c2 + c3);
+  // merge the four 4-bit masks per parity with exact FP32 arithmetic: m = ((h0 * 16 + h1) * 16 + h2) * 16 + h3
+  const uint64_t sixteen = pack_f32x2(16.f, 16.f);
+  const uint64_t acc2 = ffma2(ffma2(ffma2(h0, sixteen, h1), sixteen, h2), sixteen, h3);
+  float fe, fo;
+  unpack_f32x2(acc2, fe, fo);
+  const uint32_t me = (uint32_t)__float2int_rn(fe), mo = (uint32_t)__float2int_rn(fo);   // bit (15 - j/2) <-> column j (even) / j+1 (odd)
+  const int csub = __popc(me) + __popc(mo);
   st.cnt += csub;
-  if (csub > 0.5f) st.cand |= gbit;
+  if (csub) {
+    st.cand |= gbit;
+    st.col = col0 + (me ? 2 * (__clz(me) - 16) : 2 * (__clz(mo) - 16) + 1);   // column of a set bit
+  }
 }
 
 // DT > 0: e_dim known at compile time (strides, trip counts and index masks become immediates and the
@@ -535,7 +567,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     const int wq = w >> 2;              // 0 = owner of these rows, 1..EPQ-1 = helpers (they split the columns)
     const int r = quarter * 32 + lane;  // tile row == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t mask = p.index_mask;
     uint32_t q = 0;
     STAT_DECL(5);
 #ifdef DVQ_TC_STATS
@@ -548,7 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int slot = (int)(it & 1);
       const uint32_t sph = (uint32_t)((it >> 1) & 1);
       RowState st;
-      st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0.f; st.col = 0; st.cand = 0u;
+      st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0; st.col = 0; st.cand = 0u;
       float band = 0.f;
       bool ok = true;
       for (int c = 0; c < nchunks; ++c, ++q) {
@@ -568,7 +599,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           uint32_t v[32];
           tc::tmem_ld32(tbase + (uint32_t)sc * 32u, v);
           tmem_ld_wait_dep(v);
-          filter_subchunk(v, mask, c * 256 + sc * 32, 1u << ((c * 8 + sc) >> p.cand_gshift), band, st);
+          filter_subchunk(v, c * 256 + sc * 32, 1u << ((c * 8 + sc) >> p.cand_gshift), band, st);
         }
         tc::tc_fence_before();
         warp_arrive(&bar_acc_empty[t]);
@@ -582,14 +613,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_empty[0], fph ^ 1u, errw, ERR_FIN); STAT_ADD(1); if (!w_ok) break; }
         fin_key[r] = st.m1;
         reinterpret_cast<int*>(fin_key + TM)[r] = st.col;
-        fin_key[2 * TM + r] = st.cnt;
+        reinterpret_cast<int*>(fin_key + 2 * TM)[r] = st.cnt;
         reinterpret_cast<uint32_t*>(fin_key + 3 * TM)[r] = st.cand;
         warp_arrive(&bar_fin_full[0]);
       } else {
         { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_full[0], fph, errw, ERR_FIN); STAT_ADD(2); if (!w_ok) break; }
         // merge the helpers' states: keep the smaller minimum; the loser's minimum either falls inside
         // the winner's band (ambiguous) or voids the loser's count entirely
-        float m1 = st.m1, cnt = st.cnt;
+        float m1 = st.m1;
+        int cnt = st.cnt;
         int col = st.col;
         uint32_t cand = st.cand;
         bool flag = false;
@@ -598,7 +630,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           const float* fin_key = fin_base + h * 4 * TM;
           const float ko = fin_key[r];
           const int co = reinterpret_cast<const int*>(fin_key + TM)[r];
-          const float no = fin_key[2 * TM + r];
+          const int no = reinterpret_cast<const int*>(fin_key + 2 * TM)[r];
           const uint32_t cando = reinterpret_cast<const uint32_t*>(fin_key + 3 * TM)[r];
           if (ko < m1) {
             flag = (m1 - ko <= band);
@@ -610,7 +642,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           }
         }
         warp_arrive(&bar_fin_empty[0]);
-        flag = flag || (cnt > 0.5f);
+        flag = flag || (cnt > 0);
         if (band < 0.f) { flag = true; cand = 0xffffffffu; }   // degenerate row: every group is a candidate
         const bool valid = r < rows;
         flag = flag && valid;
