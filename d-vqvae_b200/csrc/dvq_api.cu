@@ -235,6 +235,27 @@ int dvq_vq_read_counters(const void* workspace, int64_t N, int K, int D, int fla
                                     "epi4.wait_fin_empty", "epi0.wait_fin_full", "epi0.wait_sidx_empty", "epi0.total",
                                     "gather.wait_sidx_full", "gather.total"};
     for (int i = 0; i < 14; ++i) fprintf(stderr, "[dvq tc stats] %-28s %14llu cycles (sum over CTAs)\n", names[i], st[i]);
+    if (N >= 65536) {   // pipeline timeline of CTA 3, tiles 8..11 (see TRACE in vq_tc_sm100.cu)
+      static long long tr[5 * 8 * 8];
+      DVQ_CUDA_CHECK(cudaMemcpy(tr, static_cast<const char*>(workspace) + w.off_rowlist + (size_t)(N - 8192) * sizeof(int), sizeof(tr),
+                                cudaMemcpyDeviceToHost));
+      static const char* ev[5][4] = {{"mma.a_full", "mma.acc_empty", "mma.issued", "mma.complete"},
+                                     {"own.acc_full", "own.chunk_done", "own.fin_full", "own.sidx_out"},
+                                     {"hlp.acc_full", "hlp.chunk_done", "hlp.fin_out", ""},
+                                     {"cnv.stage_full", "cnv.pass1_done", "cnv.a_empty", "cnv.a_full_out"},
+                                     {"gth.sidx_full", "gth.done", "", ""}};
+      long long base = tr[(0 * 8 + 0) * 8 + 0];
+      for (int role = 0; role < 5; ++role)
+        for (int e = 0; e < 4; ++e) {
+          if (!ev[role][e][0]) continue;
+          fprintf(stderr, "[dvq tc trace] %-16s", ev[role][e]);
+          for (int k = 0; k < 8; ++k) {
+            const long long v = tr[(role * 8 + e) * 8 + k];
+            fprintf(stderr, " %7lld", v ? v - base : -1);
+          }
+          fprintf(stderr, "\n");
+        }
+    }
   }
   return DVQ_OK;
 }

@@ -127,6 +127,62 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- the same primitives on 32-bit shared-window addresses ------------------------------------------
+// (a kernel that keeps all its barriers in one shared struct addresses them as base + constant, which
+//  saves the generic->shared conversion (S2R + LEA) at every arrive / wait site)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(100000u)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ int lds_volatile_a(uint32_t addr) {
+  int v;
+  asm volatile("ld.volatile.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile_a(uint32_t addr, int v) {
+  asm volatile("st.volatile.shared::cta.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// bounded wait, lean fast path: one try_wait + branch when the phase has already completed; the error
+// word is polled only every 64 failed tries
+__device__ __forceinline__ bool mbar_wait_a(uint32_t bar, uint32_t parity, uint32_t err_addr, int code) {
+  if (mbar_try_wait_a(bar, parity)) return true;
+#pragma unroll 1
+  for (uint32_t spin = 1; spin < (1u << 18); ++spin) {
+    if (mbar_try_wait_a(bar, parity)) return true;
+    if ((spin & 63u) == 0u && lds_volatile_a(err_addr) != 0) return false;
+  }
+  sts_volatile_a(err_addr, code);
+  return false;
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_keep_a(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -32,6 +32,7 @@
 // epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays resident in
 // shared memory for the life of the CTA.
 #include <cuda_fp16.h>
+#include <cstddef>
 
 #include "dvq_common.cuh"
 #include "tc_prims.cuh"
@@ -50,6 +51,10 @@ constexpr int GATHER_WARPS = 4;
 constexpr int NUM_WARPS = GATHER_WARP0 + GATHER_WARPS;
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int META_SLOTS = 4;
+// true: A row = [zh | zl | fold] (22-bit z, two products per code); false: A row = [zh | fold] and the exact norm
+// of the dropped residual enters the error bound (about twice the band, hence twice the undecided rows, for
+// 44 % fewer tensor-core k-steps and shared-memory operand reads)
+constexpr bool USE_ZL = false;
 
 enum ErrCode { ERR_STAGE_FULL = 1, ERR_STAGE_EMPTY, ERR_A_FULL, ERR_A_EMPTY, ERR_ACC_FULL, ERR_ACC_EMPTY, ERR_B_FULL, ERR_FIN, ERR_SIDX };
 
@@ -77,7 +82,6 @@ struct TcParams {
   int* row_list;
   int* cand_list;       // candidate-group mask of each listed row (bit g = codes [32*g<<gshift, ...))
   int cand_gshift;
-  uint32_t index_mask;  // 0xffffffe0 (kept in a register so key packing is one LOP3)
   unsigned long long* stats;   // optional wait-time accounting (DVQ_TC_STATS builds)
   int64_t ntiles;
 };
@@ -90,7 +94,7 @@ struct SmemLayout {
 
 __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   SmemLayout L;
-  const uint32_t kc_b = (uint32_t)(D + 16) / 8, kc_a = (uint32_t)(2 * D + 16) / 8;
+  const uint32_t kc_b = (uint32_t)(D + 16) / 8, kc_a = (uint32_t)((USE_ZL ? 2 : 1) * D + 16) / 8;
   L.bchunk_bytes = kc_b * 256u * 16u;
   L.bimg_bytes = 2u * L.bchunk_bytes;
   L.hist_in_smem = K <= 512 ? 1u : 0u;   // larger histograms go straight to global atomics (shared memory is full)
@@ -196,11 +200,6 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
   asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
-__device__ __forceinline__ uint32_t pack_key(uint32_t v, uint32_t mask, uint32_t j) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(v), "r"(mask), "r"(j));   // (v & mask) | j
-  return r;
-}
 // tcgen05.wait::ld that also carries a register dependence on the loaded values, so the compiler
 // cannot move their consumers above the wait
 __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
@@ -212,21 +211,38 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
                :
                : "memory");
 }
-// whole-warp wait: every lane sleeps on the barrier (try_wait with a suspend hint wakes on completion);
-// bounded, so a protocol bug sets the error word instead of hanging the GPU
-__device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volatile int* errw, int code) {
-  uint32_t spins = 0;
-  while (!tc::mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 16) || *errw != 0) {
-      if (*errw == 0) *errw = code;
-      break;
-    }
-  }
-  return *errw == 0;
-}
-__device__ __forceinline__ void warp_arrive(uint64_t* bar) {   // one arrival per warp, after all lanes are done
+__device__ __forceinline__ void warp_arrive(uint32_t bar) {   // one arrival per warp, after all lanes are done
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) tc::mbar_arrive(bar);
+  if ((threadIdx.x & 31) == 0) tc::mbar_arrive_a(bar);
+}
+// Hardware named barriers for the warp <-> warp hand-offs: a warp blocked in bar.sync issues nothing
+// (an mbarrier poll loop was measured to burn ~19 % of the SM's issue slots).  bar.arrive / bar.sync
+// order the participants' shared-memory accesses (PTX producer/consumer pattern).  `nthreads` counts
+// arrivers + waiters.  mbarriers remain only where the async proxy signals (bulk copies, tcgen05.commit).
+__device__ __forceinline__ void nb_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// Bounded mbarrier wait; a protocol bug records its code and traps (a loud launch failure, never a hang).
+__device__ __forceinline__ void wait_or_trap(uint32_t bar, uint32_t parity, int* err_out, int code) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 n;\n\t"
+      "mov.b32 n, 0;\n\t"
+      "DVQ_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "@p bra DVQ_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, %4;\n\t"
+      "@p bra DVQ_WAIT;\n\t"
+      "DVQ_DONE:\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(100000u), "r"(1u << 22)
+      : "memory");
+  if (!ok) {
+    *err_out = code;
+    __threadfence_system();
+    __trap();
+  }
 }
 
 // Optional wait-time accounting (build with DVQ_TC_STATS=1): cycles spent in each wait site,
@@ -246,6 +262,17 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {   // one arrival pe
 #define STAT_ADD(i)
 #define STAT_FLUSH(n, base)
 #endif
+// Pipeline timeline (DVQ_TC_STATS builds): clock64 stamps of one CTA for tiles 8..11, written to the unused
+// tail of the refine row list (role, event, tile, chunk); printed by dvq_vq_read_counters.
+#ifdef DVQ_TC_STATS
+#define TRACE(role, ev, c_)                                                                                         \
+  do {                                                                                                              \
+    if (blockIdx.x == 3 && (threadIdx.x & 31) == 0 && it >= 8 && it < 12 && p.N >= 65536)                            \
+      reinterpret_cast<long long*>(p.row_list + p.N - 8192)[((role) * 8 + (ev)) * 8 + (int)(it - 8) * 2 + (c_)] = clock64(); \
+  } while (0)
+#else
+#define TRACE(role, ev, c_)
+#endif
 
 // float(h) - a in one FHADD (PTX mixed-precision sub, sm_100+): h is one half of a packed pair
 __device__ __forceinline__ float half_minus_float(uint32_t h16, float a) {
@@ -254,12 +281,38 @@ __device__ __forceinline__ float half_minus_float(uint32_t h16, float a) {
   return r;
 }
 
+// All barriers live in one shared struct so that a site addresses its barrier as base + immediate.
+enum BarId { B_STAGE_FULL = 0, B_STAGE_EMPTY = 2, B_ACC_FULL = 4, B_B_FULL = 6, B_B_EMPTY = 8, B_A_EMPTY = 10, NBARS = 12 };
+// named barrier ids (0 is __syncthreads).  The accumulator-full relay has one barrier per (stage, warp group):
+// the helper warps of a tile must not wait for the owner warps, which are still merging / writing the previous
+// tile when the helpers are ready for the next one.
+enum NamedBarId { NB_ACC_FULL_OWN = 1, NB_ACC_FULL_HLP = 3, NB_ACC_EMPTY = 5, NB_A_FULL = 7, NB_FIN_FULL = 9, NB_FIN_EMPTY = 10,
+                  NB_SIDX_FULL = 11, NB_SIDX_EMPTY = 13 };
+constexpr int NB_ACC_THREADS = 32 + EPI_WARPS * 32;          // MMA warp + epilogue warps
+constexpr int NB_ACC_OWN_THREADS = 32 + 4 * 32;              // MMA warp + owner warps
+constexpr int NB_ACC_HLP_THREADS = 32 + (EPI_WARPS - 4) * 32;   // MMA warp + helper warps
+constexpr int NB_A_THREADS = 32 + 128;                       // MMA warp + converter warps
+constexpr int NB_FIN_THREADS = EPI_WARPS * 32;               // owners + helpers
+constexpr int NB_SIDX_THREADS = 4 * 32 + GATHER_WARPS * 32;  // owner epilogue warps + gather warps
+struct Ctl {
+  uint64_t bars[NBARS];
+  uint32_t tmem_slot;
+};
+#define BAR(id, i) (bar0 + 8u * (uint32_t)((id) + (i)))
+
 struct RowState {   // per (row, column subset) running result of the filter
   float m1;         // smallest accumulator value so far
   int cnt;          // number of OTHER keys within `band` of m1 (a superset count)
-  int col;          // global code index of m1 (meaningful when the row is decided: cnt == 0)
+  uint32_t bits;    // indicator mask of the last sub-chunk that held a key inside the band: even columns in the
+                    // high half, odd columns in the low half, bit 15 - j/2 of a half <-> column j
+  int col0;         // first code of that sub-chunk
   uint32_t cand;    // groups of sub-chunks holding a key within `band` of m1 (superset; always holds m1's own)
 };
+// code index of a set bit of the mask (for a decided row the only set bit is the minimum itself)
+__device__ __forceinline__ int row_state_col(const RowState& st) {
+  const int zc = __clz(st.bits);                   // 0..15: even column 2*zc; 16..31: odd column 2*(zc-16)+1
+  return st.col0 + (zc < 16 ? 2 * zc : 2 * zc - 31);
+}
 
 // packed f32x2 helpers (Blackwell FFMA2: two FP32 FMAs per issued instruction)
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
@@ -319,13 +372,9 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
   const uint64_t acc2 = ffma2(ffma2(ffma2(h0, sixteen, h1), sixteen, h2), sixteen, h3);
   float fe, fo;
   unpack_f32x2(acc2, fe, fo);
-  const uint32_t me = (uint32_t)__float2int_rn(fe), mo = (uint32_t)__float2int_rn(fo);   // bit (15 - j/2) <-> column j (even) / j+1 (odd)
-  const int csub = __popc(me) + __popc(mo);
-  st.cnt += csub;
-  if (csub) {
-    st.cand |= gbit;
-    st.col = col0 + (me ? 2 * (__clz(me) - 16) : 2 * (__clz(mo) - 16) + 1);   // column of a set bit
-  }
+  const uint32_t bits = ((uint32_t)__float2int_rn(fe) << 16) | (uint32_t)__float2int_rn(fo);
+  st.cnt += __popc(bits);
+  if (bits) { st.cand |= gbit; st.bits = bits; st.col0 = col0; }   // three predicated moves; the position is decoded once per row
 }
 
 // DT > 0: e_dim known at compile time (strides, trip counts and index masks become immediates and the
@@ -333,10 +382,13 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
 template <int DT, bool TRAIN>
 __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_stage_full[2], bar_stage_empty[2], bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2], bar_b_full[2], bar_b_empty[2];
-  __shared__ uint64_t bar_fin_full[2], bar_fin_empty[2], bar_sidx_full[2], bar_sidx_empty[2];
-  __shared__ uint32_t tmem_slot;
-  __shared__ int serr;
+  __shared__ __align__(8) Ctl ctl;   // every mbarrier + the error word: addressed as base + constant
+  // the opaque move keeps the window addresses in registers (the compiler otherwise rematerialises the
+  // generic->shared conversion, S2R + LEA, at every use)
+  uint32_t bar0, smem0;
+  asm volatile("mov.u32 %0, %1;" : "=r"(bar0) : "r"(tc::smem_u32(ctl.bars)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(smem0) : "r"(tc::smem_u32(smem)));
+  int* const err_out = p.counters + 1;
 
   const int D = DT > 0 ? DT : p.D;
   const int K = p.K;
@@ -345,22 +397,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   const int nk = D / 16;                       // k-steps per product
   const int nchunks = (K + 255) / 256;         // accumulator chunks per tile
   const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int64_t total_chunks = my_tiles * nchunks;
 
   if (tid == 0) {
-    serr = 0;
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&bar_stage_full[i], 1);
-      tc::mbar_init(&bar_stage_empty[i], 4);    // one arrival per converter warp
-      tc::mbar_init(&bar_a_full[i], 128);       // every converter thread (after its own proxy fence)
-      tc::mbar_init(&bar_a_empty[i], 1);
-      tc::mbar_init(&bar_acc_full[i], 1);
-      tc::mbar_init(&bar_acc_empty[i], EPI_WARPS);   // one arrival per epilogue warp
-      tc::mbar_init(&bar_fin_full[i], 4 * (EPQ - 1));   // helper epilogue warps -> the owner warp of the rows
-      tc::mbar_init(&bar_fin_empty[i], 4);
-      tc::mbar_init(&bar_sidx_full[i], 4);      // half-0 epilogue warps -> gather warps
-      tc::mbar_init(&bar_sidx_empty[i], GATHER_WARPS);
-      tc::mbar_init(&bar_b_full[i], 1);
-      tc::mbar_init(&bar_b_empty[i], 1);
+      tc::mbar_init(&ctl.bars[B_STAGE_FULL + i], 1);
+      tc::mbar_init(&ctl.bars[B_STAGE_EMPTY + i], 4);    // one arrival per converter warp
+      tc::mbar_init(&ctl.bars[B_ACC_FULL + i], 1);       // tcgen05.commit
+      tc::mbar_init(&ctl.bars[B_B_FULL + i], 1);
+      tc::mbar_init(&ctl.bars[B_B_EMPTY + i], 1);
+      tc::mbar_init(&ctl.bars[B_A_EMPTY + i], 1);        // tcgen05.commit
     }
     tc::fence_barrier_init();
   }
@@ -368,12 +414,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     int* shist = reinterpret_cast<int*>(smem + L.hist);
     for (int k = tid; k < K; k += NTHREADS) shist[k] = 0;
   }
-  if (warp == 1) tc::tmem_alloc(&tmem_slot, 512);
+  if (warp == 1) tc::tmem_alloc(&ctl.tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-  volatile int* errw = &serr;
+  const uint32_t tmem_base = ctl.tmem_slot;
 
   if (warp == 0) {
     // ===================== producer =====================
@@ -384,10 +429,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       auto load_chunk = [&](int c, int slot) {
         const uint32_t bytes = (uint32_t)(((uint32_t)(D + 16) / 8u) * 256u * 16u);
         const uint8_t* src = p.bimg + (size_t)c * bytes;
-        tc::mbar_arrive_expect_tx(&bar_b_full[slot], bytes);
+        tc::mbar_arrive_expect_tx_a(BAR(B_B_FULL, slot), bytes);
         for (uint32_t off = 0; off < bytes; off += 16384) {
           const uint32_t n = min(16384u, bytes - off);
-          tc::bulk_g2s(smem + L.bimg + (uint32_t)slot * L.bchunk_bytes + off, src + off, n, &bar_b_full[slot]);
+          tc::bulk_g2s_a(smem0 + L.bimg + (uint32_t)slot * L.bchunk_bytes + off, src + off, n, BAR(B_B_FULL, slot));
         }
       };
       if (resident) {
@@ -399,17 +444,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         const int64_t tile = blockIdx.x + it * gridDim.x;
         const int s = (int)(it & 1);
         const uint32_t ph = (uint32_t)((it >> 1) & 1);
-        { STAT_T0(); const bool w_ok = tc::mbar_wait(&bar_stage_empty[s], ph ^ 1u, errw, ERR_STAGE_EMPTY); STAT_ADD(0); if (!w_ok) break; }
+        { STAT_T0(); wait_or_trap(BAR(B_STAGE_EMPTY, s), ph ^ 1u, err_out, ERR_STAGE_EMPTY); STAT_ADD(0); }
         const int64_t row0 = tile * TM;
         const int rows = (int)min((int64_t)TM, p.N - row0);
         const uint32_t bytes = (uint32_t)rows * D * 4;
-        tc::mbar_arrive_expect_tx(&bar_stage_full[s], bytes);
-        if (TRAIN) tc::bulk_g2s_keep(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
-        else tc::bulk_g2s(smem + L.stage[s], p.z + row0 * D, bytes, &bar_stage_full[s]);
+        tc::mbar_arrive_expect_tx_a(BAR(B_STAGE_FULL, s), bytes);
+        if (TRAIN) tc::bulk_g2s_keep_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
+        else tc::bulk_g2s_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
         if (!resident) {
           for (int c = 0; c < nchunks; ++c, ++qb) {
             const int slot = (int)(qb & 1u);
-            if (!tc::mbar_wait(&bar_b_empty[slot], ((qb >> 1) & 1u) ^ 1u, errw, ERR_B_FULL)) break;
+            wait_or_trap(BAR(B_B_EMPTY, slot), ((qb >> 1) & 1u) ^ 1u, err_out, ERR_B_FULL);
             load_chunk(c, slot);
           }
         }
@@ -417,58 +462,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       STAT_FLUSH(1, 0);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      bool ok = true;
+    // ===================== MMA issuer (whole warp; lane 0 issues) =====================
+    // In order per chunk: wait for the accumulator stage (named barrier, epilogue -> MMA), issue, wait for
+    // the completion mbarrier of this chunk's tcgen05.commit and relay it to the 12 epilogue warps through a
+    // named barrier, so that only this warp ever polls.  The next chunk is issued after the relay: with
+    // two TMEM stages and an epilogue that takes longer per chunk than the MMAs, the tensor pipe is
+    // never the one waited for.
+    {
       const bool resident = nchunks <= 2;
-      if (resident) for (int c = 0; c < nchunks; ++c) ok = ok && tc::mbar_wait(&bar_b_full[c], 0, errw, ERR_B_FULL);
+      if (resident) for (int c = 0; c < nchunks; ++c) wait_or_trap(BAR(B_B_FULL, c), 0, err_out, ERR_B_FULL);
       const uint32_t b_lbo = 256u * 16u, b_sbo = 128;
       const uint32_t a_lbo = A_CHUNK_BYTES, a_sbo = 128;
       // descriptors are (address >> 4) in the low bits: advancing by one k-step (two 8-wide k-chunks)
       // is a constant add that never carries out of the 14-bit address field
       const uint64_t a_step = (uint64_t)((2u * a_lbo) >> 4), b_step = (uint64_t)((2u * b_lbo) >> 4);
-      const uint64_t a_desc0[2] = {tc::make_smem_desc(tc::smem_u32(smem + L.a_img[0]), a_lbo, a_sbo),
-                                   tc::make_smem_desc(tc::smem_u32(smem + L.a_img[1]), a_lbo, a_sbo)};
-      const uint64_t b_desc0 = tc::make_smem_desc(tc::smem_u32(smem + L.bimg), b_lbo, b_sbo);
+      // descriptors from the un-laundered window address: warp-uniform values the compiler keeps in uniform
+      // registers, so each tcgen05.mma issues without a per-lane operand broadcast loop
+      const uint32_t sbase = tc::smem_u32(smem);
+      const uint64_t a_desc0 = tc::make_smem_desc(sbase + L.a_img[0], a_lbo, a_sbo);
+      const uint64_t a_desc1 = tc::make_smem_desc(sbase + L.a_img[1], a_lbo, a_sbo);
+      const uint64_t b_desc0 = tc::make_smem_desc(sbase + L.bimg, b_lbo, b_sbo);
+      const uint32_t barbase = tc::smem_u32(ctl.bars);
       uint32_t q = 0;
       STAT_DECL(3);
 #ifdef DVQ_TC_STATS
       const long long mma_t0 = clock64();
 #endif
-      for (int64_t it = 0; ok && it < my_tiles; ++it) {
+      for (int64_t it = 0; it < my_tiles; ++it) {
         const int a = (int)(it & 1);
-        { STAT_T0(); const bool w_ok = tc::mbar_wait(&bar_a_full[a], (uint32_t)((it >> 1) & 1), errw, ERR_A_FULL); STAT_ADD(0); if (!w_ok) break; }
-        tc::tc_fence_after();
+        { STAT_T0(); nb_sync(NB_A_FULL + a, NB_A_THREADS); STAT_ADD(0); }
+        TRACE(0, 0, 0);
         for (int c = 0; c < nchunks; ++c, ++q) {
           const uint32_t t = q & 1u;
-          { STAT_T0(); const bool w_ok = tc::mbar_wait(&bar_acc_empty[t], ((q >> 1) & 1u) ^ 1u, errw, ERR_ACC_EMPTY); STAT_ADD(1); if (!w_ok) { ok = false; break; } }
+          if (q >= 2) { STAT_T0(); nb_sync(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS); STAT_ADD(1); }
           tc::tc_fence_after();
+          TRACE(0, 1, c & 1);
           const int n = min(256, K - c * 256);
           const uint32_t idesc = tc::make_idesc_f16(128, n, 0);
           const uint32_t d_tmem = tmem_base + t * 256u;
           const uint32_t bslot = resident ? (uint32_t)c : (q & 1u);
-          if (!resident) {
-            if (!tc::mbar_wait(&bar_b_full[bslot], (q >> 1) & 1u, errw, ERR_B_FULL)) { ok = false; break; }
+          if (!resident) wait_or_trap(BAR(B_B_FULL, bslot), (q >> 1) & 1u, err_out, ERR_B_FULL);
+          if (tc::elect_one()) {
+            const uint64_t bc = b_desc0 + (uint64_t)((bslot * L.bchunk_bytes) >> 4);
+            uint64_t ad = a ? a_desc1 : a_desc0, bd = bc;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < nk; ++j) {   // zh . eh
+              tc::umma_f16(d_tmem, ad, bd, idesc, acc);
+              acc = 1; ad += a_step; bd += b_step;
+            }
+            if (USE_ZL) {
+              bd = bc;
+#pragma unroll
+              for (int j = 0; j < nk; ++j) {   // zl . eh  (A holds -zl: negate-A bit 13 of the descriptor)
+                tc::umma_f16(d_tmem, ad, bd, idesc | (1u << 13), 1);
+                ad += a_step; bd += b_step;
+              }
+            }
+            tc::umma_f16(d_tmem, ad, bd, idesc, 1);   // fold columns
+            tc::umma_commit_a(barbase + 8u * (B_ACC_FULL + t));
+            if (!resident) tc::umma_commit_a(barbase + 8u * (B_B_EMPTY + bslot));   // ring slot free once these MMAs have read it
+            if (c == nchunks - 1) tc::umma_commit_a(barbase + 8u * (uint32_t)(B_A_EMPTY + a));  // every MMA of this tile done: A image free
           }
-          const uint64_t bc = b_desc0 + (uint64_t)((bslot * L.bchunk_bytes) >> 4);
-          uint64_t ad = a ? a_desc0[1] : a_desc0[0], bd = bc;
-          uint32_t acc = 0;
-#pragma unroll 1
-          for (int j = 0; j < nk; ++j) {   // zh . eh
-            tc::umma_f16(d_tmem, ad, bd, idesc, acc);
-            acc = 1; ad += a_step; bd += b_step;
-          }
-          bd = bc;
-#pragma unroll 1
-          for (int j = 0; j < nk; ++j) {   // zl . eh  (A holds -zl: negate-A bit 13 of the descriptor)
-            tc::umma_f16(d_tmem, ad, bd, idesc | (1u << 13), 1);
-            ad += a_step; bd += b_step;
-          }
-          tc::umma_f16(d_tmem, ad, bd, idesc, 1);   // fold columns
-          tc::umma_commit(&bar_acc_full[t]);
-          if (!resident) tc::umma_commit(&bar_b_empty[bslot]);   // ring slot free once these MMAs have read it
+          __syncwarp();
+          TRACE(0, 2, c & 1);
+          wait_or_trap(BAR(B_ACC_FULL, t), (q >> 1) & 1u, err_out, ERR_ACC_FULL);
+          TRACE(0, 3, c & 1);
+          tc::tc_fence_before();
+          nb_arrive(NB_ACC_FULL_HLP + (int)t, NB_ACC_HLP_THREADS);
+          nb_arrive(NB_ACC_FULL_OWN + (int)t, NB_ACC_OWN_THREADS);
         }
-        tc::umma_commit(&bar_a_empty[a]);
       }
 #ifdef DVQ_TC_STATS
       stat_acc[2] = clock64() - mma_t0;
@@ -489,7 +552,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int s = (int)(it & 1), a = (int)(it & 1);
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
       const int rows = (int)min((int64_t)TM, p.N - tile * TM);
-      { STAT_T0(); const bool w_ok = warp_wait(&bar_stage_full[s], ph, errw, ERR_STAGE_FULL); STAT_ADD(0); if (!w_ok) break; }
+      { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), ph, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
+      if (warp == CONV_WARP0) TRACE(3, 0, 0);
       const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nv;
       // pass 1: squared norm (lane-rotated chunk order: conflict-free 128-bit reads)
       float nsq = 0.f;
@@ -514,14 +578,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const float f0a = __half2float(__float2half_ru(2.f * zs * (1.f + 1.f / 128.f)));
       const float fr = (s_n == 0.f) ? 0.f : exp2f((float)rexp);
       const float bias2 = 2.f * f0a * cb.b0;
-      const float eps = zs * cb.delta_max * (1.f + 1.f / 64.f)
-                      + (zs * (1.f / 4194304.f) + sqrtf((float)D) * (1.f / 33554432.f)) * cb.eh_norm_bound
-                      + bias2 * ((float)(2 * nk + 3) * (1.f / 1048576.f))      // tensor-core FP32 accumulation
-                      + bias2 * (1.f / 262144.f)                               // 5 packed index bits
-                      + 16.f * fr * (1.f / 256.f);                             // ee rounding (r_n = fr / 256)
-      float band = 2.f * eps * (1.f + 1.f / 16.f);
-      if (degenerate) band = -1.f;    // marks "send to the exact kernel"
-      { STAT_T0(); const bool w_ok = warp_wait(&bar_a_empty[a], ph ^ 1u, errw, ERR_A_EMPTY); STAT_ADD(1); if (!w_ok) break; }
+      float eps = zs * cb.delta_max * (1.f + 1.f / 64.f)
+                + bias2 * ((float)((USE_ZL ? 2 : 1) * nk + 3) * (1.f / 1048576.f))      // tensor-core FP32 accumulation
+                + 16.f * fr * (1.f / 256.f);                                            // ee rounding (r_n = fr / 256)
+      if (USE_ZL) eps += (zs * (1.f / 4194304.f) + sqrtf((float)D) * (1.f / 33554432.f)) * cb.eh_norm_bound;   // zl rounding
+      float rsq = 0.f;   // !USE_ZL: exact squared norm of the residual z' - zh that the product drops
+      if (warp == CONV_WARP0) TRACE(3, 1, 0);
+      { STAT_T0(); wait_or_trap(BAR(B_A_EMPTY, a), ph ^ 1u, err_out, ERR_A_EMPTY); STAT_ADD(1); }
+      if (warp == CONV_WARP0) TRACE(3, 2, 0);
       // pass 2: convert and write the A image
       uint8_t* aimg = smem + L.a_img[a] + (r >> 3) * 128 + (r & 7) * 16;
       for (int i = 0; i < nv / 2; ++i) {
@@ -535,25 +599,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         for (int e = 0; e < 4; ++e) {
           hi[e] = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
           const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi[e]);
-          lo[e] = __floats2half2_rn(half_minus_float(hb & 0xffffu, x[2 * e]), half_minus_float(hb >> 16, x[2 * e + 1]));
+          const float r0 = half_minus_float(hb & 0xffffu, x[2 * e]), r1 = half_minus_float(hb >> 16, x[2 * e + 1]);   // exact
+          if (USE_ZL) lo[e] = __floats2half2_rn(r0, r1);
+          else rsq = fmaf(r1, r1, fmaf(r0, r0, rsq));
         }
         *reinterpret_cast<uint4*>(aimg + (size_t)c8 * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(hi);
-        *reinterpret_cast<uint4*>(aimg + (size_t)(nv / 2 + c8) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(lo);
+        if (USE_ZL) *reinterpret_cast<uint4*>(aimg + (size_t)(nv / 2 + c8) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(lo);
       }
+      if (!USE_ZL) eps += sqrtf(rsq) * (1.f + 1e-4f) * cb.eh_norm_bound;
+      float band = 2.f * eps * (1.f + 1.f / 16.f);
+      if (degenerate) band = -1.f;    // marks "send to the exact kernel"
+      constexpr int kFold = USE_ZL ? 2 : 1;   // fold k-chunks follow the zh (and zl) chunks
       {
         __half2 f[4];
         f[0] = __floats2half2_rn(f0a, fr);
         f[1] = __floats2half2_rn(fr, fr);
         f[2] = __floats2half2_rn(0.f, 0.f);
         f[3] = f[2];
-        *reinterpret_cast<uint4*>(aimg + (size_t)(nv) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
+        *reinterpret_cast<uint4*>(aimg + (size_t)(kFold * nv / 2) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
         f[0] = f[2]; f[1] = f[2];
-        *reinterpret_cast<uint4*>(aimg + (size_t)(nv + 1) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
+        *reinterpret_cast<uint4*>(aimg + (size_t)(kFold * nv / 2 + 1) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
       }
       reinterpret_cast<float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r] = band;
-      warp_arrive(&bar_stage_empty[s]);       // staging slot may be refilled
+      warp_arrive(BAR(B_STAGE_EMPTY, s));       // staging slot may be refilled
       tc::fence_proxy_async_smem();           // A image visible to the tensor core (async proxy)
-      tc::mbar_arrive(&bar_a_full[a]);
+      nb_arrive(NB_A_FULL + a, NB_A_THREADS);
+      if (warp == CONV_WARP0) TRACE(3, 3, 0);
     }
 #ifdef DVQ_TC_STATS
     stat_acc[2] = clock64() - conv_t0;
@@ -577,16 +648,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int64_t row0 = tile * TM;
       const int rows = (int)min((int64_t)TM, p.N - row0);
       const int slot = (int)(it & 1);
-      const uint32_t sph = (uint32_t)((it >> 1) & 1);
       RowState st;
-      st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0; st.col = 0; st.cand = 0u;
+      st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0; st.bits = 0u; st.col0 = 0; st.cand = 0u;
       float band = 0.f;
-      bool ok = true;
       for (int c = 0; c < nchunks; ++c, ++q) {
         const uint32_t t = q & 1u;
-        if (ok) { STAT_T0(); ok = warp_wait(&bar_acc_full[t], (q >> 1) & 1u, errw, ERR_ACC_FULL); STAT_ADD(0); }
-        if (!ok) continue;
+        {
+          STAT_T0();
+          if (wq == 0) nb_sync(NB_ACC_FULL_OWN + (int)t, NB_ACC_OWN_THREADS);
+          else nb_sync(NB_ACC_FULL_HLP + (int)t, NB_ACC_HLP_THREADS);
+          STAT_ADD(0);
+        }
         tc::tc_fence_after();
+        if (w == 0) TRACE(1, 0, c & 1);
+        if (w == 4) TRACE(2, 0, c & 1);
         if (c == 0) band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
         const int n = min(256, K - c * 256);
         const uint32_t tbase = tmem_base + lane_addr + t * 256u;
@@ -602,27 +677,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           filter_subchunk(v, c * 256 + sc * 32, 1u << ((c * 8 + sc) >> p.cand_gshift), band, st);
         }
         tc::tc_fence_before();
-        warp_arrive(&bar_acc_empty[t]);
+        if (w == 0) TRACE(1, 1, c & 1);
+        if (w == 4) TRACE(2, 1, c & 1);
+        if ((int64_t)q + 2 < total_chunks) nb_arrive(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS);
       }
-      if (*errw) break;
       float* fin_base = reinterpret_cast<float*>(smem + L.fin);   // single slot: phase flips every tile
-      const uint32_t fph = (uint32_t)(it & 1);
       if (wq > 0) {
         // hand this warp's partial result to the owner warp of the same rows
         float* fin_key = fin_base + (wq - 1) * 4 * TM;
-        { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_empty[0], fph ^ 1u, errw, ERR_FIN); STAT_ADD(1); if (!w_ok) break; }
+        if (it >= 1) { STAT_T0(); nb_sync(NB_FIN_EMPTY, NB_FIN_THREADS); STAT_ADD(1); }
         fin_key[r] = st.m1;
-        reinterpret_cast<int*>(fin_key + TM)[r] = st.col;
+        reinterpret_cast<int*>(fin_key + TM)[r] = row_state_col(st);
         reinterpret_cast<int*>(fin_key + 2 * TM)[r] = st.cnt;
         reinterpret_cast<uint32_t*>(fin_key + 3 * TM)[r] = st.cand;
-        warp_arrive(&bar_fin_full[0]);
+        nb_arrive(NB_FIN_FULL, NB_FIN_THREADS);
+        if (w == 4) TRACE(2, 2, 0);
       } else {
-        { STAT_T0(); const bool w_ok = warp_wait(&bar_fin_full[0], fph, errw, ERR_FIN); STAT_ADD(2); if (!w_ok) break; }
+        { STAT_T0(); nb_sync(NB_FIN_FULL, NB_FIN_THREADS); STAT_ADD(2); }
+        if (w == 0) TRACE(1, 2, 0);
         // merge the helpers' states: keep the smaller minimum; the loser's minimum either falls inside
         // the winner's band (ambiguous) or voids the loser's count entirely
         float m1 = st.m1;
         int cnt = st.cnt;
-        int col = st.col;
+        int col = row_state_col(st);
         uint32_t cand = st.cand;
         bool flag = false;
 #pragma unroll
@@ -641,33 +718,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
             cand |= cando;
           }
         }
-        warp_arrive(&bar_fin_empty[0]);
+        if (it + 1 < my_tiles) nb_arrive(NB_FIN_EMPTY, NB_FIN_THREADS);
         flag = flag || (cnt > 0);
-        if (band < 0.f) { flag = true; cand = 0xffffffffu; }   // degenerate row: every group is a candidate
+        if (band < 0.f) { flag = true; cand = 0x7fffffffu; }   // degenerate row: every group is a candidate
         const bool valid = r < rows;
         flag = flag && valid;
-        { STAT_T0(); const bool w_ok = warp_wait(&bar_sidx_empty[slot], sph ^ 1u, errw, ERR_SIDX); STAT_ADD(3); if (!w_ok) break; }
-        // code for the gather warps: sign bit = "undecided" (its z_q row is rewritten by the exact kernel,
-        // its SSE / histogram contribution is left to it)
-        reinterpret_cast<int*>(smem + L.sidx)[slot * TM + r] = (col * D * 4) | (flag ? 0x80000000 : 0);   // byte offset into E
-        warp_arrive(&bar_sidx_full[slot]);
+        if (it >= 2) { STAT_T0(); nb_sync(NB_SIDX_EMPTY + slot, NB_SIDX_THREADS); STAT_ADD(3); }
+        // code for the gather warps: byte offset of the code row in E, or — sign bit set — "undecided" with the
+        // candidate-group mask in the low 31 bits (the gather warps append such rows to the refine list; the
+        // exact kernel rewrites their z_q row and accounts their SSE / histogram contribution)
+        reinterpret_cast<int*>(smem + L.sidx)[slot * TM + r] = flag ? (int)(cand | 0x80000000u) : col * D * 4;
+        nb_arrive(NB_SIDX_FULL + slot, NB_SIDX_THREADS);
+        if (w == 0) TRACE(1, 3, 0);
         if (valid && !flag) {
           p.idx[row0 + r] = (int64_t)col;          // 32 lanes x 8 B: one coalesced 256-byte store per warp
           if (TRAIN) {
             if (L.hist_in_smem) atomicAdd(reinterpret_cast<int*>(smem + L.hist) + col, 1);
             else atomicAdd(p.hist + col, 1ull);   // large codebooks: contention is low, shared memory is full
-          }
-        }
-        // undecided rows -> list for the exact FP32 kernel (one atomic per warp that has any)
-        const unsigned bal = __ballot_sync(0xffffffffu, flag);
-        if (bal) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(p.counters, __popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (flag) {
-            const int pos = base + __popc(bal & ((1u << lane) - 1u));
-            p.row_list[pos] = (int)(row0 + r);
-            p.cand_list[pos] = (int)cand;
           }
         }
       }
@@ -705,9 +772,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int64_t row0 = tile * TM;
       const int rows = (int)min((int64_t)TM, p.N - row0);
       const int slot = (int)(it & 1);
-      const uint32_t sph = (uint32_t)((it >> 1) & 1);
-      { STAT_T0(); const bool w_ok = warp_wait(&bar_sidx_full[slot], sph, errw, ERR_SIDX); STAT_ADD(0); if (!w_ok) break; }
+      { STAT_T0(); nb_sync(NB_SIDX_FULL + slot, NB_SIDX_THREADS); STAT_ADD(0); }
+      if (gw == 0) TRACE(4, 0, 0);
       const int* sp = reinterpret_cast<const int*>(smem + L.sidx) + slot * TM + rbase;
+      {
+        // undecided rows of this warp's 32 rows -> list for the exact FP32 kernel (one atomic per warp that has any)
+        const int code = reinterpret_cast<const int*>(smem + L.sidx)[slot * TM + gw * rows_per_warp + lane];
+        const bool und = code < 0 && lane < rows_per_warp && gw * rows_per_warp + lane < rows;
+        const unsigned bal = __ballot_sync(0xffffffffu, und);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(p.counters, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (und) {
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            p.row_list[pos] = (int)(row0 + gw * rows_per_warp + lane);
+            p.cand_list[pos] = code & 0x7fffffff;
+          }
+        }
+      }
       float lsse = 0.f;
       const bool full_tile = rows == TM;
 #pragma unroll 1
@@ -726,7 +809,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
             for (int u = 0; u < U; ++u) kk[u] = sp[(t0 + u) * rps];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              e4[u] = __ldg(reinterpret_cast<const float4*>(ec + (uint32_t)(kk[u] & 0x7fffffff)));
+              e4[u] = __ldg(reinterpret_cast<const float4*>(ec + (uint32_t)max(kk[u], 0)));   // undecided: any valid row
               if (TRAIN) z4[u] = __ldcs(reinterpret_cast<const float4*>(zp + (int64_t)((t0 + u) * rps) * D));   // last use of this tile
             }
 #pragma unroll
@@ -748,7 +831,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
             const int ro = t * rps;
             if (rbase + ro >= rows) continue;
             const int kv = sp[ro];
-            const float4 e1 = __ldg(reinterpret_cast<const float4*>(ec + (uint32_t)(kv & 0x7fffffff)));
+            const float4 e1 = __ldg(reinterpret_cast<const float4*>(ec + (uint32_t)max(kv, 0)));
             float4 o4 = e1;
             if (TRAIN) {
               const float4 z1 = __ldcs(reinterpret_cast<const float4*>(zp + (int64_t)ro * D));
@@ -762,7 +845,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           }
         }
       }
-      warp_arrive(&bar_sidx_empty[slot]);
+      if (gw == 0) TRACE(4, 1, 0);
+      if (it + 2 < my_tiles) nb_arrive(NB_SIDX_EMPTY + slot, NB_SIDX_THREADS);
       sse_acc += (double)lsse;
     }
 #ifdef DVQ_TC_STATS
@@ -786,7 +870,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       if (hcount) atomicAdd(p.hist + k, (unsigned long long)hcount);
     }
   }
-  if (tid == 0 && serr) atomicExch(p.counters + 1, serr);
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
@@ -799,9 +882,9 @@ bool vq_tc_supported(int64_t N, int K, int D) {
   return smem_layout(K, D).total + 128 + 512 <= 227 * 1024;   // + alignment slack + static barriers
 }
 
-int vq_tc_cand_gshift(int K) {   // 32 candidate bits cover K/32 sub-chunks in groups of 2^gshift
+int vq_tc_cand_gshift(int K) {   // 31 candidate bits (bit 31 is the "undecided" flag of the hand-off word) cover K/32 sub-chunks in groups of 2^gshift
   int g = 0;
-  while (((K + 31) / 32 + (1 << g) - 1) >> g > 32) ++g;
+  while (((K + 31) / 32 + (1 << g) - 1) >> g > 31) ++g;
   return g;
 }
 
@@ -830,7 +913,6 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   TcParams p;
   p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.N = N; p.K = K; p.D = D; p.train = train;
   p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list; p.cand_list = cand_list; p.cand_gshift = vq_tc_cand_gshift(K);
-  p.index_mask = 0xffffffe0u;
   p.stats = reinterpret_cast<unsigned long long*>(counters + 8);
   p.ntiles = (N + TM - 1) / TM;
   const size_t smem = L.total + 128;
