@@ -8,15 +8,17 @@
 // exactly the index the all-FP32 kernel would give it (the true minimiser is always inside the
 // candidate groups: every key outside the band is provably farther).
 //
-// The codebook is staged once per CTA in shared memory with a (D+1)-float row pitch (conflict-free
-// for lane = code); each undecided row then costs ~2 groups x 64 FMAs per lane instead of the
-// K x D of the full kernel.
+// The codebook is staged once per CTA in shared memory with a (D+4)-float row pitch: 16-byte aligned
+// rows whose 128-bit reads are conflict-free for lane = code (a quarter-warp covers all 32 banks).  The
+// z row stays in shared memory too (broadcast 128-bit reads), so a thread needs ~40 registers and 32
+// warps per SM hide the latency of the sequential FMA chain; each undecided row then costs ~2 groups
+// x (32 LDS.128 + 64 FMAs) per lane instead of the K x D of the full kernel.
 #include "dvq_common.cuh"
 
 namespace dvq {
 namespace {
 
-constexpr int RTHREADS = 512;
+constexpr int RTHREADS = 1024;
 
 template <int DT, bool TRAIN, bool SMEM_E>
 __global__ void __launch_bounds__(RTHREADS, 1)
@@ -25,7 +27,7 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
                  double* __restrict__ sse, const int* __restrict__ row_list, const int* __restrict__ cand_list,
                  const int* __restrict__ n_list, int gshift) {
   extern __shared__ __align__(16) float smem_f[];   // zbuf[warps][2][DT] | es[K][DT+1] when SMEM_E
-  constexpr int PITCH = DT + 1;
+  constexpr int PITCH = DT + 4;
   constexpr int NW = RTHREADS / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* zbuf = smem_f + warp * 2 * DT;             // double-buffered z row of this warp
@@ -33,9 +35,7 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
   if (SMEM_E) {
     for (int i = tid; i < K * (DT / 4); i += RTHREADS) {
       const int k = i / (DT / 4), d = (i - k * (DT / 4)) * 4;
-      const float4 v = ldg4(E + (size_t)k * DT + d);
-      float* dst = es + k * PITCH + d;
-      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      *reinterpret_cast<float4*>(es + k * PITCH + d) = ldg4(E + (size_t)k * DT + d);
     }
     __syncthreads();
   }
@@ -61,26 +61,20 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
     __syncwarp();
     const int64_t row = row_list[i];
     const unsigned cand = (unsigned)cand_list[i];
-    const float* zrow = z + row * DT;
-    float zr[DT];
-#pragma unroll
-    for (int d = 0; d < DT; d += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(zbuf + buf * DT + d);   // broadcast read
-      zr[d] = v.x; zr[d + 1] = v.y; zr[d + 2] = v.z; zr[d + 3] = v.w;
-    }
+    const float* zb = zbuf + buf * DT;
     float s2 = 0.f;   // ||z||^2 exactly as vq_simt_fp32.cu computes it
 #pragma unroll
     for (int c = 0; c < DT; c += 32) {
-      float v = 0.f;
-#pragma unroll
-      for (int d = 0; d < 32; ++d) v = (lane == d) ? zr[c + d] : v;   // zr[c + lane] without dynamic register indexing
-      if (c + lane < DT) s2 = fmaf(v, v, s2);
+      if (c + lane < DT) { const float v = zb[c + lane]; s2 = fmaf(v, v, s2); }
     }
     const float zz = warp_sum(s2);
     float best = INFINITY;
     int bidx = 0;
-    for (int g = 0; g < groups; ++g) {
-      if (!((cand >> g) & 1u)) continue;
+    unsigned todo = cand ? cand : 0xffffffffu;
+    if (groups < 32) todo &= (1u << groups) - 1u;
+    while (todo) {                       // set bits in ascending order = groups in ascending code order
+      const int g = __ffs(todo) - 1;
+      todo &= todo - 1u;
       for (int sc = g << gshift; sc < ((g + 1) << gshift) && sc * 32 < K; ++sc) {
         const int code = sc * 32 + lane;
         float dist = INFINITY;
@@ -89,14 +83,20 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
           if (SMEM_E) {
             const float* er = es + code * PITCH;
 #pragma unroll
-            for (int d = 0; d < DT; ++d) acc = fmaf(zr[d], er[d], acc);
+            for (int d = 0; d < DT; d += 4) {
+              const float4 e4 = *reinterpret_cast<const float4*>(er + d);
+              const float4 z4 = *reinterpret_cast<const float4*>(zb + d);   // broadcast read
+              acc = fmaf(z4.x, e4.x, acc); acc = fmaf(z4.y, e4.y, acc);
+              acc = fmaf(z4.z, e4.z, acc); acc = fmaf(z4.w, e4.w, acc);
+            }
           } else {
             const float* er = E + (int64_t)code * DT;
 #pragma unroll
             for (int d = 0; d < DT; d += 4) {
               const float4 e4 = ldg4(er + d);
-              acc = fmaf(zr[d], e4.x, acc); acc = fmaf(zr[d + 1], e4.y, acc);
-              acc = fmaf(zr[d + 2], e4.z, acc); acc = fmaf(zr[d + 3], e4.w, acc);
+              const float4 z4 = *reinterpret_cast<const float4*>(zb + d);
+              acc = fmaf(z4.x, e4.x, acc); acc = fmaf(z4.y, e4.y, acc);
+              acc = fmaf(z4.z, e4.z, acc); acc = fmaf(z4.w, e4.w, acc);
             }
           }
           dist = __fmaf_rn(-2.0f, acc, __fadd_rn(zz, __ldg(ee + code)));
@@ -131,7 +131,6 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
       if (TRAIN) atomicAdd(hist + bidx, 1ull);
     }
     __syncwarp();   // everyone is done with zbuf[buf] before the next-but-one prefetch overwrites it
-    (void)zrow;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (TRAIN) {
@@ -152,7 +151,7 @@ int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int
   if (rc) return rc;
   if (D != 64) return fail(DVQ_ERR_BAD_SHAPE, "candidate refine kernel is instantiated for e_dim 64 only");
   const size_t zbuf_bytes = (size_t)(RTHREADS / 32) * 2 * 64 * sizeof(float);
-  const size_t smem_e = (size_t)K * (64 + 1) * sizeof(float);
+  const size_t smem_e = (size_t)K * (64 + 4) * sizeof(float);
   const bool in_smem = smem_e + zbuf_bytes <= 200 * 1024;
 #define DVQ_LAUNCH_REFINE(TR_, SM_)                                                                                      \
   do {                                                                                                                   \
