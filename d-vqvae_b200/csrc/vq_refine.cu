@@ -72,43 +72,74 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
     int bidx = 0;
     unsigned todo = cand ? cand : 0xffffffffu;
     if (groups < 32) todo &= (1u << groups) - 1u;
-    while (todo) {                       // set bits in ascending order = groups in ascending code order
-      const int g = __ffs(todo) - 1;
-      todo &= todo - 1u;
-      for (int sc = g << gshift; sc < ((g + 1) << gshift) && sc * 32 < K; ++sc) {
-        const int code = sc * 32 + lane;
-        float dist = INFINITY;
-        if (code < K) {
-          float acc = 0.f;
-          if (SMEM_E) {
-            const float* er = es + code * PITCH;
-#pragma unroll
-            for (int d = 0; d < DT; d += 4) {
-              const float4 e4 = *reinterpret_cast<const float4*>(er + d);
-              const float4 z4 = *reinterpret_cast<const float4*>(zb + d);   // broadcast read
-              acc = fmaf(z4.x, e4.x, acc); acc = fmaf(z4.y, e4.y, acc);
-              acc = fmaf(z4.z, e4.z, acc); acc = fmaf(z4.w, e4.w, acc);
-            }
-          } else {
-            const float* er = E + (int64_t)code * DT;
-#pragma unroll
-            for (int d = 0; d < DT; d += 4) {
-              const float4 e4 = ldg4(er + d);
-              const float4 z4 = *reinterpret_cast<const float4*>(zb + d);
-              acc = fmaf(z4.x, e4.x, acc); acc = fmaf(z4.y, e4.y, acc);
-              acc = fmaf(z4.z, e4.z, acc); acc = fmaf(z4.w, e4.w, acc);
-            }
-          }
-          dist = __fmaf_rn(-2.0f, acc, __fadd_rn(zz, __ldg(ee + code)));
+    // candidate sub-chunks (32 codes each) in ascending code order, two at a time: one broadcast read of z
+    // feeds both dot products, and the two sequential FMA chains interleave
+    int g_sc = 0, g_end = 0;
+    auto next_sc = [&]() -> int {   // warp-uniform; -1 when exhausted
+      for (;;) {
+        if (g_sc < g_end) {
+          const int r = g_sc++;
+          if (r * 32 < K) return r;
+          g_sc = g_end;
+          continue;
         }
-        int k = code;
+        if (!todo) return -1;
+        const int g = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        g_sc = g << gshift;
+        g_end = (g + 1) << gshift;
+      }
+    };
+    // lexicographic (distance, code) minimum over the warp: monotone integer image of the distance, one
+    // REDUX.MIN, then the lowest lane holding the minimum (= lowest code: exact ties keep the first index)
+    auto warp_argmin = [&](float dist, int sc, float& best_, int& bidx_) {
+      const uint32_t b = __float_as_uint(dist);
+      const uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);   // NaN-free input: order-preserving
+      const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+      const unsigned who = __ballot_sync(0xffffffffu, key == kmin);
+      const int src = __ffs(who) - 1;
+      const float dmin = __shfl_sync(0xffffffffu, dist, src);
+      if (dmin < best_) { best_ = dmin; bidx_ = sc * 32 + src; }
+    };
+    for (;;) {
+      const int sa = next_sc();
+      if (sa < 0) break;
+      const int sb = next_sc();
+      const int code_a = sa * 32 + lane, code_b = (sb < 0 ? sa : sb) * 32 + lane;
+      const bool va = code_a < K, vb = sb >= 0 && code_b < K;
+      float acc_a = 0.f, acc_b = 0.f;
+      if (SMEM_E) {
+        const float* ea = es + (va ? code_a : 0) * PITCH;
+        const float* eb = es + (vb ? code_b : 0) * PITCH;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float od = __shfl_xor_sync(0xffffffffu, dist, o);
-          const int ok = __shfl_xor_sync(0xffffffffu, k, o);
-          if (od < dist || (od == dist && ok < k)) { dist = od; k = ok; }
+        for (int d = 0; d < DT; d += 4) {
+          const float4 z4 = *reinterpret_cast<const float4*>(zb + d);   // broadcast read
+          const float4 a4 = *reinterpret_cast<const float4*>(ea + d);
+          const float4 b4 = *reinterpret_cast<const float4*>(eb + d);
+          acc_a = fmaf(z4.x, a4.x, acc_a); acc_b = fmaf(z4.x, b4.x, acc_b);
+          acc_a = fmaf(z4.y, a4.y, acc_a); acc_b = fmaf(z4.y, b4.y, acc_b);
+          acc_a = fmaf(z4.z, a4.z, acc_a); acc_b = fmaf(z4.z, b4.z, acc_b);
+          acc_a = fmaf(z4.w, a4.w, acc_a); acc_b = fmaf(z4.w, b4.w, acc_b);
         }
-        if (dist < best) { best = dist; bidx = k; }   // groups visited in ascending code order
+      } else {
+        const float* ea = E + (int64_t)(va ? code_a : 0) * DT;
+        const float* eb = E + (int64_t)(vb ? code_b : 0) * DT;
+#pragma unroll
+        for (int d = 0; d < DT; d += 4) {
+          const float4 z4 = *reinterpret_cast<const float4*>(zb + d);
+          const float4 a4 = ldg4(ea + d);
+          const float4 b4 = ldg4(eb + d);
+          acc_a = fmaf(z4.x, a4.x, acc_a); acc_b = fmaf(z4.x, b4.x, acc_b);
+          acc_a = fmaf(z4.y, a4.y, acc_a); acc_b = fmaf(z4.y, b4.y, acc_b);
+          acc_a = fmaf(z4.z, a4.z, acc_a); acc_b = fmaf(z4.z, b4.z, acc_b);
+          acc_a = fmaf(z4.w, a4.w, acc_a); acc_b = fmaf(z4.w, b4.w, acc_b);
+        }
+      }
+      const float dist_a = va ? __fmaf_rn(-2.0f, acc_a, __fadd_rn(zz, __ldg(ee + code_a))) : INFINITY;
+      warp_argmin(dist_a, sa, best, bidx);
+      if (sb >= 0) {
+        const float dist_b = vb ? __fmaf_rn(-2.0f, acc_b, __fadd_rn(zz, __ldg(ee + code_b))) : INFINITY;
+        warp_argmin(dist_b, sb, best, bidx);
       }
     }
     // outputs for this row (vq_simt_fp32.cu's epilogue)
