@@ -8,29 +8,33 @@
 // with power-of-two scales s_n (per row) and s_E (per codebook) that put every operand inside the
 // FP16 range, ee_k = ||e_k||^2 and the bias B_n >= 2 |z_n| max_k|e_k| which keeps acc >= 0.
 // It is ONE chain of tcgen05.mma (kind::f16, FP32 accumulate in TMEM, M=128, N<=256, K=16):
-//     A row  = [ zh (D) | zl (D) | fold (16) ]     zh = fp16(z'), zl = fp16(z' - zh)  (22-bit z)
-//     B row  = [ eh (D) |          fold (16) ]     eh = fp16(-2 e')
-// issued as zh.eh + zl.eh + fold.fold; the fold columns carry g_n*B_n and g_n*ee_k as products of
-// FP16 pairs (ee_k split in three FP16 terms).  Because acc >= 0 its bit pattern is monotone, so the
-// epilogue reduces raw accumulators with 3-input FMNMX3 minima and recovers the winning column from the
+//     A row  = [ zh (D) | fold (16) ]     zh = fp16(z')      (USE_ZL adds zl = fp16(z' - zh) as a second product)
+//     B row  = [ eh (D) | fold (16) ]     eh = fp16(-2 e')
+// issued as zh.eh + fold.fold; the fold columns carry g_n*B_n and g_n*ee_k as products of FP16 pairs
+// (ee_k split in three FP16 terms).  Because acc >= 0 its bit pattern is monotone, so the epilogue
+// reduces raw accumulators with 3-input FMNMX3 minima and recovers the winning column from the
 // indicator bit masks of its ambiguity count (no per-element index packing).
 //
 // Rigor.  eps_n bounds |acc - exact| for every k of row n (operand rounding: |z'| * max_k||eh_k+2e'_k||
-// measured exactly by the prep kernel; FP16 lo-term rounding; tensor-core FP32 accumulation;
-// index packing; ee rounding).  A row is decided iff no other key lies within 2*eps_n of the
-// minimum; the count of such keys is kept with a running (never too small) threshold, exact
-// resets, and FFMA.SAT arithmetic on the FMA pipe.  Undecided rows (a few %) go to the list.
+// measured exactly by the prep kernel; ||z' - zh|| * max_k||eh_k|| measured exactly by the converter;
+// tensor-core FP32 accumulation; ee rounding).  A row is decided iff no other key lies within
+// 2*eps_n of the minimum; the count of such keys is kept with a running (never too small) threshold,
+// exact resets, and FFMA.SAT / FFMA2 arithmetic on the FMA pipe.  Undecided rows (a few %) go to the list.
 //
 // Pipeline (one persistent CTA per SM, 22 warps; every SM sub-partition hosts 1 converter, 3 epilogue
-// and 1 gather warp — a lone warp issues only ~1 instruction per 5 cycles, so work is spread wide):
-//   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B)
-//   warp 1      MMA      : single elected thread issues tcgen05.mma, commits to mbarriers
-//   warps 2-5   convert  : staging -> registers -> scales / norms / bounds -> FP16 A image (2 stages)
-//   warps 6-17  epilogue : tcgen05.ld TMEM (software-pipelined) -> keys -> argmin + ambiguity count
-//   warps 18-21 gather   : E[idx] (128-bit, 8-16 loads in flight per lane), z_q, SSE, smem histogram, idx
-// TMEM: 512 columns = 2 accumulator stages of 256, so the MMA of one 256-code chunk overlaps the
-// epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays resident in
-// shared memory for the life of the CTA.
+// and 1 gather warp):
+//   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B),
+//                          codebook chunks -> 2-slot ring when K > 512
+//   warp 1      MMA      : one elected lane issues tcgen05.mma from uniform-register descriptors; the warp
+//                          then waits for the chunk's commit mbarrier and relays it on named barriers
+//   warps 2-5   convert  : staging -> scales / norms / bounds -> FP16 A image (2 stages)
+//   warps 6-17  epilogue : tcgen05.ld TMEM -> min tree + ambiguity masks per 32-code sub-chunk; three warps
+//                          per TMEM lane quarter split the columns, the owner merges and writes idx / histogram
+//   warps 18-21 gather   : E[idx] (128-bit, 8-16 loads in flight per lane), z_q, SSE, refine-list append
+// Warp-to-warp hand-offs are hardware named barriers (bar.arrive / bar.sync), mbarriers only where the
+// async proxy signals.  TMEM: 512 columns = 2 accumulator stages of 256, so the MMA of one 256-code
+// chunk overlaps the epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays
+// resident in shared memory for K <= 512 and is streamed per row tile above.
 #include <cuda_fp16.h>
 #include <cstddef>
 
