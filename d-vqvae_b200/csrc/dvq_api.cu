@@ -87,6 +87,7 @@ VqWorkspace vq_workspace_layout(int64_t N, int K, int D, int flags) {
   w.off_bop = off;
   if (may_tc) off = align_up(off + vq_tc_operand_bytes(K, D), 1024);
   w.off_rowmeta = off;
+  if (may_tc) off = align_up(off + vq_tc_rownorm_bytes(N, D), 256);
   w.total = off;
   return w;
 }
@@ -190,21 +191,29 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
       int* row_list = reinterpret_cast<int*>(ws + w.off_rowlist);
       int* cand_list = reinterpret_cast<int*>(ws + w.off_rowlist + align_up(sizeof(int) * (size_t)N, 256));
       profile_mark(1, true, s);
-      rc = launch_vq_tc(z, E, ee, N, K, D, train, z_q, idx, hist, sse, ws + w.off_bop, counters, row_list, cand_list, s);
+      float* row_nsq = vq_tc_rownorm_bytes(N, D) ? reinterpret_cast<float*>(ws + w.off_rowmeta) : nullptr;
+      rc = launch_vq_tc(z, E, ee, N, K, D, train, z_q, idx, hist, sse, ws + w.off_bop, row_nsq, counters, row_list, cand_list, s);
       profile_mark(1, false, s);
       if (rc) return rc;
       // exact FP32 refine of the rows the filter flagged (device-side count, no host sync): restricted to
       // the recorded candidate groups when that kernel covers the shape, else the full FP32 kernel on the list
       profile_mark(2, true, s);
-      if (vq_refine_supported(K, D))
-        rc = launch_vq_refine(z, E, ee, K, D, train, z_q, idx, hist, sse, row_list, cand_list, counters, vq_tc_cand_gshift(K), s);
-      else
-        rc = launch_vq_simt(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, counters, s);
+      // (large codebooks: rows with too many candidates for the list record, and degenerate rows, sit in a second
+      //  list stored downwards from the end of the same buffer; both kernels re-evaluate them against every code)
+      const bool list_mode = vq_tc_cand_gshift(K) < 0;
+      if (vq_refine_supported(K, D)) {
+        rc = launch_vq_refine(z, E, ee, K, D, train, z_q, idx, hist, sse, row_list, cand_list, counters, vq_tc_cand_gshift(K),
+                              list_mode ? row_list + (N - 1) : nullptr, list_mode ? counters + 2 : nullptr, s);
+      } else {
+        rc = launch_vq_simt(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, counters, 1, s);
+        if (!rc && list_mode)
+          rc = launch_vq_simt(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list + (N - 1), counters + 2, -1, s);
+      }
       profile_mark(2, false, s);
       if (rc) return rc;
     } else {
       profile_mark(1, true, s);
-      rc = launch_vq_simt(z, E, ee, N, K, D, train, z_q, idx, hist, sse, nullptr, nullptr, s);
+      rc = launch_vq_simt(z, E, ee, N, K, D, train, z_q, idx, hist, sse, nullptr, nullptr, 1, s);
       profile_mark(1, false, s);
       if (rc) return rc;
     }

@@ -41,7 +41,7 @@ struct VqWorkspace {
   size_t off_counters;  // int   [8]            refine-list length, overflow flags
   size_t off_rowlist;   // int   [2][N]         rows the tensor-core filter could not decide + their candidate masks
   size_t off_bop;       // operand image of the codebook for the tcgen05 path
-  size_t off_rowmeta;   // float [N]            (reserved)
+  size_t off_rowmeta;   // float [N]            ||z_n||^2 for the sliced tcgen05 path (e_dim > 64), else empty
   size_t total;
 };
 VqWorkspace vq_workspace_layout(int64_t N, int K, int D, int flags);
@@ -54,21 +54,22 @@ int launch_code_norms(const float* E, int K, int D, float* ee, cudaStream_t s);
 // row_list[0 .. *n_list) (device-side count), used as the refine stage of the tcgen05 path.
 int launch_vq_simt(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
                    float* z_q, int64_t* idx, unsigned long long* hist, double* sse,
-                   const int* row_list, const int* n_list, cudaStream_t s);
+                   const int* row_list, const int* n_list, int list_stride, cudaStream_t s);
 
 // tcgen05 filter kernel (vq_tc_sm100.cu); supported(K,D) says whether the shape is handled.
 bool vq_tc_supported(int64_t N, int K, int D);
 size_t vq_tc_operand_bytes(int K, int D);
+size_t vq_tc_rownorm_bytes(int64_t N, int D);
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
                  float* z_q, int64_t* idx, unsigned long long* hist, double* sse,
-                 void* bop, int* counters, int* row_list, int* cand_list, cudaStream_t s);
+                 void* bop, float* row_nsq, int* counters, int* row_list, int* cand_list, cudaStream_t s);
 
 // candidate-restricted exact refine (vq_refine.cu); cand_list[i] = bit mask of 32*2^gshift-code groups
 bool vq_refine_supported(int K, int D);
 int vq_tc_cand_gshift(int K);
 int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int D, int train, float* z_q, int64_t* idx,
                      unsigned long long* hist, double* sse, const int* row_list, const int* cand_list,
-                     const int* n_list, int gshift, cudaStream_t s);
+                     const int* n_list, int gshift, const int* ovf_last, const int* n_ovf, cudaStream_t s);
 
 int launch_onehot(const int64_t* idx, int64_t N, int K, float* onehot, cudaStream_t s);
 int launch_finalize(const unsigned long long* hist, const double* sse, int64_t N, int K, int D, float al,

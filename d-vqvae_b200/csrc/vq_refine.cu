@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(RTHREADS, 1)
 vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ ee, int K,
                  float* __restrict__ zq, int64_t* __restrict__ idx_out, unsigned long long* __restrict__ hist,
                  double* __restrict__ sse, const int* __restrict__ row_list, const int* __restrict__ cand_list,
-                 const int* __restrict__ n_list, int gshift) {
+                 const int* __restrict__ n_list, int gshift, const int* __restrict__ ovf_last, const int* __restrict__ n_ovf) {
   extern __shared__ __align__(16) float smem_f[];   // zbuf[warps][2][DT] | es[K][DT+1] when SMEM_E
   constexpr int PITCH = DT + 4;
   constexpr int NW = RTHREADS / 32;
@@ -42,16 +42,42 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
   const int n = *n_list;
   const int wglobal = blockIdx.x * NW + warp;
   const int wtotal = gridDim.x * NW;
-  const int groups = ((K + 31) / 32 + (1 << gshift) - 1) >> gshift;   // candidate bits in use
+  const bool list_mode = gshift < 0;   // candidates as up to three (sub-chunk index + 1) entries of 10 bits, see vq_tc_sm100.cu
+  const int nsc = (K + 31) / 32;
+  const int groups = list_mode ? 0 : (nsc + (1 << gshift) - 1) >> gshift;   // candidate bits in use
   double lsse = 0.0;
   // cp.async prefetch of the next undecided row of this warp hides its (random-access) global latency
   auto prefetch = [&](int i, int buf) {
-    if (i < n && lane < DT / 4) {
-      const float* src = z + (int64_t)row_list[i] * DT + lane * 4;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(zbuf + buf * DT + lane * 4);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    if (i < n) {
+      const float* src = z + (int64_t)row_list[i] * DT;
+#pragma unroll
+      for (int v = lane; v < DT / 4; v += 32) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(zbuf + buf * DT + v * 4);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + v * 4) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // outputs of one row (vq_simt_fp32.cu's epilogue), executed by one warp
+  auto emit_row = [&](int64_t row, int bidx, const float* zsrc) {
+    float* orow = zq + row * DT;
+    const float* erow = E + (int64_t)bidx * DT;
+    for (int c = lane * 4; c < DT; c += 128) {
+      const float4 e4 = ldg4(erow + c);
+      float4 o4 = e4;
+      if (TRAIN) {
+        const float4 z4 = *reinterpret_cast<const float4*>(zsrc + c);
+        const float dx = __fsub_rn(e4.x, z4.x), dy = __fsub_rn(e4.y, z4.y);
+        const float dz = __fsub_rn(e4.z, z4.z), dw = __fsub_rn(e4.w, z4.w);
+        lsse += (double)dx * dx + (double)dy * dy + (double)dz * dz + (double)dw * dw;
+        o4 = make_float4(__fadd_rn(z4.x, dx), __fadd_rn(z4.y, dy), __fadd_rn(z4.z, dz), __fadd_rn(z4.w, dw));
+      }
+      *reinterpret_cast<float4*>(orow + c) = o4;
+    }
+    if (lane == 0) {
+      idx_out[row] = (int64_t)bidx;
+      if (TRAIN) atomicAdd(hist + bidx, 1ull);
+    }
   };
   prefetch(wglobal, 0);
   int buf = 0;
@@ -70,11 +96,27 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
     const float zz = warp_sum(s2);
     float best = INFINITY;
     int bidx = 0;
-    unsigned todo = cand ? cand : 0xffffffffu;
-    if (groups < 32) todo &= (1u << groups) - 1u;
     // candidate sub-chunks (32 codes each) in ascending code order, two at a time: one broadcast read of z
     // feeds both dot products, and the two sequential FMA chains interleave
-    int g_sc = 0, g_end = 0;
+    unsigned todo = 0u;
+    int g_sc = 0, g_end = 0, l0 = -1, l1 = -1, l2 = -1;
+    if (list_mode) {
+      if (cand == 0u || cand == 0x3fffffffu) { g_end = nsc; }   // overflow / degenerate: every code
+      else {
+        l0 = (int)(cand & 1023u) - 1; l1 = (int)((cand >> 10) & 1023u) - 1; l2 = (int)((cand >> 20) & 1023u) - 1;
+        // ascending order, empty entries (-1) last
+        const int big = 1 << 30;
+        int a0 = l0 < 0 ? big : l0, a1 = l1 < 0 ? big : l1, a2 = l2 < 0 ? big : l2;
+        int t;
+        if (a0 > a1) { t = a0; a0 = a1; a1 = t; }
+        if (a1 > a2) { t = a1; a1 = a2; a2 = t; }
+        if (a0 > a1) { t = a0; a0 = a1; a1 = t; }
+        l0 = a0 == big ? -1 : a0; l1 = a1 == big ? -1 : a1; l2 = a2 == big ? -1 : a2;
+      }
+    } else {
+      todo = cand ? cand : 0xffffffffu;
+      if (groups < 32) todo &= (1u << groups) - 1u;
+    }
     auto next_sc = [&]() -> int {   // warp-uniform; -1 when exhausted
       for (;;) {
         if (g_sc < g_end) {
@@ -82,6 +124,11 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
           if (r * 32 < K) return r;
           g_sc = g_end;
           continue;
+        }
+        if (list_mode) {
+          const int r = l0;
+          l0 = l1; l1 = l2; l2 = -1;
+          return (r >= 0 && r * 32 < K) ? r : -1;
         }
         if (!todo) return -1;
         const int g = __ffs(todo) - 1;
@@ -142,28 +189,68 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
         warp_argmin(dist_b, sb, best, bidx);
       }
     }
-    // outputs for this row (vq_simt_fp32.cu's epilogue)
-    float* orow = zq + row * DT;
-    const float* erow = E + (int64_t)bidx * DT;
-    for (int c = lane * 4; c < DT; c += 128) {
-      const float4 e4 = ldg4(erow + c);
-      float4 o4 = e4;
-      if (TRAIN) {
-        const float4 z4 = *reinterpret_cast<const float4*>(zbuf + buf * DT + c);
-        const float dx = __fsub_rn(e4.x, z4.x), dy = __fsub_rn(e4.y, z4.y);
-        const float dz = __fsub_rn(e4.z, z4.z), dw = __fsub_rn(e4.w, z4.w);
-        lsse += (double)dx * dx + (double)dy * dy + (double)dz * dz + (double)dw * dw;
-        o4 = make_float4(__fadd_rn(z4.x, dx), __fadd_rn(z4.y, dy), __fadd_rn(z4.z, dz), __fadd_rn(z4.w, dw));
-      }
-      *reinterpret_cast<float4*>(orow + c) = o4;
-    }
-    if (lane == 0) {
-      idx_out[row] = (int64_t)bidx;
-      if (TRAIN) atomicAdd(hist + bidx, 1ull);
-    }
+    emit_row(row, bidx, zbuf + buf * DT);
     __syncwarp();   // everyone is done with zbuf[buf] before the next-but-one prefetch overwrites it
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // ---- overflow rows (list mode: more than three candidate sub-chunks, degenerate rows): one CTA per row, the
+  //      warps split the sub-chunks of the whole codebook, lexicographic (distance, code) minimum across warps ----
+  if (n_ovf != nullptr) {
+    __shared__ float red_d[NW];
+    __shared__ int red_k[NW];
+    const int n2 = *n_ovf;
+    float* zrow = smem_f;   // every warp is done with its z buffers after the barrier below
+    for (int j = blockIdx.x; j < n2; j += gridDim.x) {
+      __syncthreads();
+      const int64_t row = ovf_last[-(int64_t)j];   // the list is stored downwards from the end of the buffer
+      for (int v = tid; v < DT / 4; v += RTHREADS) reinterpret_cast<float4*>(zrow)[v] = ldg4(z + row * DT + v * 4);
+      __syncthreads();
+      float s2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < DT; c += 32) {
+        if (c + lane < DT) { const float v = zrow[c + lane]; s2 = fmaf(v, v, s2); }
+      }
+      const float zz = warp_sum(s2);
+      float best = INFINITY;
+      int bidx = 0x7fffffff;
+      for (int sc = warp; sc < nsc; sc += NW) {
+        const int code = sc * 32 + lane;
+        float dist = INFINITY;
+        if (code < K) {
+          const float* er = SMEM_E ? es + code * PITCH : E + (int64_t)code * DT;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int d = 0; d < DT; d += 4) {
+            const float4 z4 = *reinterpret_cast<const float4*>(zrow + d);
+            const float4 e4 = SMEM_E ? *reinterpret_cast<const float4*>(er + d) : ldg4(er + d);
+            acc = fmaf(z4.x, e4.x, acc); acc = fmaf(z4.y, e4.y, acc);
+            acc = fmaf(z4.z, e4.z, acc); acc = fmaf(z4.w, e4.w, acc);
+          }
+          dist = __fmaf_rn(-2.0f, acc, __fadd_rn(zz, __ldg(ee + code)));
+        }
+        const uint32_t b = __float_as_uint(dist);
+        const uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+        const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+        const int src = __ffs(__ballot_sync(0xffffffffu, key == kmin)) - 1;
+        const float dmin = __shfl_sync(0xffffffffu, dist, src);
+        if (dmin < best) { best = dmin; bidx = sc * 32 + src; }
+      }
+      if (lane == 0) { red_d[warp] = best; red_k[warp] = bidx; }
+      __syncthreads();
+      if (warp == 0) {
+        float d = red_d[lane];
+        int k = red_k[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, d, o);
+          const int ok = __shfl_xor_sync(0xffffffffu, k, o);
+          if (od < d || (od == d && ok < k)) { d = od; k = ok; }
+        }
+        if (k == 0x7fffffff) k = 0;
+        emit_row(row, k, zrow);
+      }
+    }
+  }
   if (TRAIN) {
     lsse = warp_sum(lsse);
     if (lane == 0 && lsse != 0.0) atomicAdd(sse, lsse);
@@ -172,24 +259,21 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
 
 }  // namespace
 
-bool vq_refine_supported(int K, int D) { return D == 64 && K >= 32; }
+bool vq_refine_supported(int K, int D) { return (D == 16 || D == 32 || D == 64 || D == 128 || D == 256) && K >= 32; }
 
-int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int D, int train, float* z_q, int64_t* idx,
-                     unsigned long long* hist, double* sse, const int* row_list, const int* cand_list,
-                     const int* n_list, int gshift, cudaStream_t s) {
-  DeviceProps dp;
-  int rc = device_props(&dp);
-  if (rc) return rc;
-  if (D != 64) return fail(DVQ_ERR_BAD_SHAPE, "candidate refine kernel is instantiated for e_dim 64 only");
-  const size_t zbuf_bytes = (size_t)(RTHREADS / 32) * 2 * 64 * sizeof(float);
-  const size_t smem_e = (size_t)K * (64 + 4) * sizeof(float);
+template <int DT>
+static int launch_refine_dt(const float* z, const float* E, const float* ee, int K, int train, float* z_q, int64_t* idx,
+                            unsigned long long* hist, double* sse, const int* row_list, const int* cand_list,
+                            const int* n_list, int gshift, const int* ovf_last, const int* n_ovf, int sm_count, cudaStream_t s) {
+  const size_t zbuf_bytes = (size_t)(RTHREADS / 32) * 2 * DT * sizeof(float);
+  const size_t smem_e = (size_t)K * (DT + 4) * sizeof(float);
   const bool in_smem = smem_e + zbuf_bytes <= 200 * 1024;
 #define DVQ_LAUNCH_REFINE(TR_, SM_)                                                                                      \
   do {                                                                                                                   \
-    const size_t bytes = zbuf_bytes + (SM_ ? smem_e : 0);                                                                            \
-    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_refine_kernel<64, TR_, SM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
-    vq_refine_kernel<64, TR_, SM_><<<dp.sm_count, RTHREADS, bytes, s>>>(z, E, ee, K, z_q, idx, hist, sse, row_list,      \
-                                                                       cand_list, n_list, gshift);                      \
+    const size_t bytes = zbuf_bytes + (SM_ ? smem_e : 0);                                                                \
+    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_refine_kernel<DT, TR_, SM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
+    vq_refine_kernel<DT, TR_, SM_><<<sm_count, RTHREADS, bytes, s>>>(z, E, ee, K, z_q, idx, hist, sse, row_list,         \
+                                                                      cand_list, n_list, gshift, ovf_last, n_ovf);      \
   } while (0)
   if (train) { if (in_smem) DVQ_LAUNCH_REFINE(true, true); else DVQ_LAUNCH_REFINE(true, false); }
   else       { if (in_smem) DVQ_LAUNCH_REFINE(false, true); else DVQ_LAUNCH_REFINE(false, false); }
@@ -197,6 +281,22 @@ int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return DVQ_OK;
+}
+
+int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int D, int train, float* z_q, int64_t* idx,
+                     unsigned long long* hist, double* sse, const int* row_list, const int* cand_list,
+                     const int* n_list, int gshift, const int* ovf_last, const int* n_ovf, cudaStream_t s) {
+  DeviceProps dp;
+  int rc = device_props(&dp);
+  if (rc) return rc;
+  switch (D) {
+    case 16: return launch_refine_dt<16>(z, E, ee, K, train, z_q, idx, hist, sse, row_list, cand_list, n_list, gshift, ovf_last, n_ovf, dp.sm_count, s);
+    case 32: return launch_refine_dt<32>(z, E, ee, K, train, z_q, idx, hist, sse, row_list, cand_list, n_list, gshift, ovf_last, n_ovf, dp.sm_count, s);
+    case 64: return launch_refine_dt<64>(z, E, ee, K, train, z_q, idx, hist, sse, row_list, cand_list, n_list, gshift, ovf_last, n_ovf, dp.sm_count, s);
+    case 128: return launch_refine_dt<128>(z, E, ee, K, train, z_q, idx, hist, sse, row_list, cand_list, n_list, gshift, ovf_last, n_ovf, dp.sm_count, s);
+    case 256: return launch_refine_dt<256>(z, E, ee, K, train, z_q, idx, hist, sse, row_list, cand_list, n_list, gshift, ovf_last, n_ovf, dp.sm_count, s);
+    default: return fail(DVQ_ERR_BAD_SHAPE, "candidate refine kernel is instantiated for e_dim 16..256 (powers of two) only");
+  }
 }
 
 }  // namespace dvq

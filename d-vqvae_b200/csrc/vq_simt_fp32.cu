@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 vq_simt_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ ee,
                int64_t N, int K, int D, int train, float* __restrict__ zq, int64_t* __restrict__ idx_out,
                unsigned long long* __restrict__ hist, double* __restrict__ sse,
-               const int* __restrict__ row_list, const int* __restrict__ n_list) {
+               const int* __restrict__ row_list, const int* __restrict__ n_list, int list_stride) {
   __shared__ __align__(16) float zs[BK][LDT];
   __shared__ __align__(16) float es[BK][LDT];
   __shared__ int64_t srow[BM];
@@ -66,7 +66,7 @@ vq_simt_kernel(const float* __restrict__ z, const float* __restrict__ E, const f
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     if (tid < BM) {
       int64_t r = tile * BM + tid;
-      srow[tid] = r < nrows ? (row_list ? (int64_t)row_list[r] : r) : (int64_t)-1;
+      srow[tid] = r < nrows ? (row_list ? (int64_t)row_list[r * list_stride] : r) : (int64_t)-1;
     }
     __syncthreads();
     const int64_t grow0 = srow[lrow], grow1 = srow[lrow + 64];
@@ -242,7 +242,7 @@ int launch_code_norms(const float* E, int K, int D, float* ee, cudaStream_t s) {
 
 int launch_vq_simt(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
                    float* z_q, int64_t* idx, unsigned long long* hist, double* sse, const int* row_list,
-                   const int* n_list, cudaStream_t s) {
+                   const int* n_list, int list_stride, cudaStream_t s) {
   DeviceProps dp;
   int rc = device_props(&dp);
   if (rc) return rc;
@@ -253,9 +253,9 @@ int launch_vq_simt(const float* z, const float* E, const float* ee, int64_t N, i
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(E) |
                                      reinterpret_cast<uintptr_t>(z_q)) % 16 == 0);
   if (vec)
-    vq_simt_kernel<true><<<(unsigned)grid, NTHREADS, 0, s>>>(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, n_list);
+    vq_simt_kernel<true><<<(unsigned)grid, NTHREADS, 0, s>>>(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, n_list, list_stride);
   else
-    vq_simt_kernel<false><<<(unsigned)grid, NTHREADS, 0, s>>>(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, n_list);
+    vq_simt_kernel<false><<<(unsigned)grid, NTHREADS, 0, s>>>(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, n_list, list_stride);
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return DVQ_OK;

@@ -52,7 +52,9 @@ constexpr int EPQ = 3;                       // epilogue warps per TMEM lane qua
 constexpr int EPI_WARPS = 4 * EPQ;
 constexpr int GATHER_WARP0 = EPI_WARP0 + EPI_WARPS;
 constexpr int GATHER_WARPS = 4;
-constexpr int NUM_WARPS = GATHER_WARP0 + GATHER_WARPS;
+constexpr int BLOAD_WARP = GATHER_WARP0 + GATHER_WARPS;   // codebook streamer (active when the image is not resident)
+constexpr int NUM_WARPS = BLOAD_WARP + 1;
+constexpr int DSLICE = 64;                   // e_dim is contracted in slices of at most 64 columns
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int META_SLOTS = 4;
 // true: A row = [zh | zl | fold] (22-bit z, two products per code); false: A row = [zh | fold] and the exact norm
@@ -76,6 +78,7 @@ struct TcParams {
   const float* E;
   const uint8_t* bimg;
   const CbMeta* cb;
+  const float* row_nsq;   // ||z_n||^2 per row (pre-pass), only for e_dim > DSLICE
   int64_t N;
   int K, D, train;
   float* zq;
@@ -84,8 +87,8 @@ struct TcParams {
   double* sse;
   int* counters;   // [0] refine-list length, [1] protocol error code
   int* row_list;
-  int* cand_list;       // candidate-group mask of each listed row (bit g = codes [32*g<<gshift, ...))
-  int cand_gshift;
+  int* cand_list;       // candidates of each listed row: group mask (bit g = codes [32*g<<gshift, ...)) or sub-chunk list
+  int cand_gshift;      // mask mode: log2 of the sub-chunks per mask bit; -1: list mode (see cand_union)
   unsigned long long* stats;   // optional wait-time accounting (DVQ_TC_STATS builds)
   int64_t ntiles;
 };
@@ -93,28 +96,41 @@ struct TcParams {
 struct SmemLayout {
   uint32_t bimg, a_img[2], stage[2], meta, fin, sidx, hist, total;
   uint32_t bimg_bytes, a_bytes, stage_bytes;   // bimg_bytes: the 2-slot codebook ring in shared memory
-  uint32_t bchunk_bytes, hist_in_smem;           // one 256-code chunk of the operand image
+  uint32_t bchunk_bytes, hist_in_smem;           // one ring slot: (256 codes) x (one e_dim slice + the fold columns)
+  uint32_t ns, ds, a_bufs, bslice_bytes;         // e_dim = ns slices of ds columns; a slice without the fold columns
 };
+
+constexpr uint32_t SMEM_LIMIT = 227u * 1024u - 640u;   // dynamic shared memory budget (alignment slack + static barriers)
 
 __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   SmemLayout L;
-  const uint32_t kc_b = (uint32_t)(D + 16) / 8, kc_a = (uint32_t)((USE_ZL ? 2 : 1) * D + 16) / 8;
-  L.bchunk_bytes = kc_b * 256u * 16u;
+  L.ds = (uint32_t)(D < DSLICE ? D : DSLICE);
+  L.ns = (uint32_t)D / L.ds;
+  const uint32_t kc_s = L.ds / 8, kc_a = (uint32_t)((USE_ZL ? 2 : 1) * D + 16) / 8;
+  L.bslice_bytes = kc_s * 256u * 16u;
+  L.bchunk_bytes = (kc_s + 2u) * 256u * 16u;
   L.bimg_bytes = 2u * L.bchunk_bytes;
-  L.hist_in_smem = K <= 512 ? 1u : 0u;   // larger histograms go straight to global atomics (shared memory is full)
   L.a_bytes = kc_a * A_CHUNK_BYTES;
-  L.stage_bytes = (uint32_t)TM * D * 4;
-  uint32_t off = 0;
-  L.bimg = off; off += (L.bimg_bytes + 127u) & ~127u;
-  L.a_img[0] = off; off += (L.a_bytes + 127u) & ~127u;
-  L.a_img[1] = off; off += (L.a_bytes + 127u) & ~127u;
-  L.stage[0] = off; off += L.stage_bytes;
-  L.stage[1] = off; off += L.stage_bytes;
-  L.meta = off; off += META_SLOTS * TM * 4;
-  L.fin = off; off += (EPQ - 1) * TM * 16;   // (EPQ-1) helper warps x (key, col, cnt, cand); single slot
-  L.sidx = off; off += 2 * TM * 4;      // 2 slots of final code index (-1: undecided)
-  L.hist = off; off += L.hist_in_smem ? (uint32_t)K * 4 : 0u;
-  L.total = off;
+  L.stage_bytes = (uint32_t)TM * L.ds * 4;
+  // preference order when shared memory is short: drop the shared-memory histogram (global atomics), then the
+  // second A image (the converters then wait for the previous tile's MMAs)
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    L.hist_in_smem = (K <= 512 && attempt == 0) ? 1u : 0u;   // larger histograms go straight to global atomics
+    L.a_bufs = attempt < 2 ? 2u : 1u;
+    uint32_t off = 0;
+    L.bimg = off; off += (L.bimg_bytes + 127u) & ~127u;
+    L.a_img[0] = off; off += (L.a_bytes + 127u) & ~127u;
+    L.a_img[1] = L.a_bufs == 2 ? off : L.a_img[0];
+    if (L.a_bufs == 2) off += (L.a_bytes + 127u) & ~127u;
+    L.stage[0] = off; off += L.stage_bytes;
+    L.stage[1] = off; off += L.stage_bytes;
+    L.meta = off; off += META_SLOTS * TM * 4;
+    L.fin = off; off += (EPQ - 1) * TM * 16;   // (EPQ-1) helper warps x (key, col, cnt, cand); single slot
+    L.sidx = off; off += 2 * TM * 4;      // 2 slots of the hand-off word (code offset | undecided flag + candidates)
+    L.hist = off; off += L.hist_in_smem ? (uint32_t)K * 4 : 0u;
+    L.total = off;
+    if (L.total <= SMEM_LIMIT) break;
+  }
   return L;
 }
 
@@ -152,11 +168,30 @@ __global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, CbMeta* 
   }
 }
 
-// byte offset of element (code k, column d) in the global operand image: chunk-contiguous
-// [k / 256][d / 8][k % 256][d % 8] halfs, i.e. each 256-code chunk is one contiguous shared-memory image
+// byte offset of element (code k, column d) in the global operand image: one block per (256-code chunk,
+// e_dim slice), each block laid out [d' / 8][k % 256][d' % 8] halfs exactly as its shared-memory ring slot;
+// the 16 fold columns (d >= D) follow the last slice of a chunk inside the same block
 __host__ __device__ inline size_t bimg_offset(int k, int d, int D) {
-  const size_t chunk_bytes = (size_t)((D + 16) / 8) * 256 * 16;
-  return (size_t)(k >> 8) * chunk_bytes + (size_t)(d >> 3) * (256 * 16) + (size_t)(k & 255) * 16 + (size_t)(d & 7) * 2;
+  const int ds = D < DSLICE ? D : DSLICE, ns = D / ds;
+  const size_t block_bytes = (size_t)(ds / 8 + 2) * 256 * 16;
+  const int sl = d < D ? d / ds : ns - 1;
+  const int dd = d < D ? d - sl * ds : ds + (d - D);
+  return ((size_t)(k >> 8) * ns + sl) * block_bytes + (size_t)(dd >> 3) * (256 * 16) + (size_t)(k & 255) * 16 + (size_t)(dd & 7) * 2;
+}
+
+// ||z_n||^2 per row for e_dim > DSLICE (the converter needs the row scale before it sees the first slice)
+__global__ void tc_row_nsq_kernel(const float* __restrict__ z, int64_t N, int D, float* __restrict__ out) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float4* src = reinterpret_cast<const float4*>(z + row * D);
+  float acc = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = __ldg(src + i);
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
 }
 
 // one warp per code: eh = fp16(-2 s_E e), fold columns, residual norm -> atomic max
@@ -318,6 +353,19 @@ __device__ __forceinline__ int row_state_col(const RowState& st) {
   return st.col0 + (zc < 16 ? 2 * zc : 2 * zc - 31);
 }
 
+// Candidate record of a row.  Mask mode (K <= 992): bit g <-> 32-code sub-chunk g held a key inside the band.
+// List mode (larger codebooks, where 31 bits would be too coarse): up to three 10-bit entries (sub-chunk index
+// + 1, 0 = empty, packed from the low bits); CAND_OVERFLOW = more than three -> the refine scans every code.
+constexpr uint32_t CAND_OVERFLOW = 0x3fffffffu;
+template <bool LIST>
+__device__ __forceinline__ uint32_t cand_union(uint32_t a, uint32_t b) {
+  if (!LIST) return a | b;
+  if (a == CAND_OVERFLOW || b == CAND_OVERFLOW) return CAND_OVERFLOW;
+  const int na = a == 0u ? 0 : (a < 1024u ? 1 : (a < (1u << 20) ? 2 : 3));
+  const int nb = b == 0u ? 0 : (b < 1024u ? 1 : (b < (1u << 20) ? 2 : 3));
+  return na + nb > 3 ? CAND_OVERFLOW : (a | (b << (10 * na)));
+}
+
 // packed f32x2 helpers (Blackwell FFMA2: two FP32 FMAs per issued instruction)
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
@@ -341,6 +389,7 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
 //           the column of the minimum for a decided row (after the last reset the only key that was ever
 //           inside the band is the minimum itself), so no per-element index packing is needed.
 // ~3 issued instructions per element: 0.5 FMNMX3 (ALU) + 1 FFMA.SAT + 0.5 FFMA2 (FMA pipe).
+template <bool LIST>
 __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uint32_t gbit, float band, RowState& st) {
   const float BIG = 1048576.f;
   float key[32];
@@ -378,12 +427,13 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
   unpack_f32x2(acc2, fe, fo);
   const uint32_t bits = ((uint32_t)__float2int_rn(fe) << 16) | (uint32_t)__float2int_rn(fo);
   st.cnt += __popc(bits);
-  if (bits) { st.cand |= gbit; st.bits = bits; st.col0 = col0; }   // three predicated moves; the position is decoded once per row
+  if (bits) { st.cand = cand_union<LIST>(st.cand, gbit); st.bits = bits; st.col0 = col0; }   // the position is decoded once per row
 }
 
 // DT > 0: e_dim known at compile time (strides, trip counts and index masks become immediates and the
 // role loops unroll); DT == 0: generic.  TRAIN selects the straight-through / SSE / histogram epilogue.
-template <int DT, bool TRAIN>
+// LIST selects the candidate record of the undecided rows (see cand_union): sub-chunk list for large codebooks.
+template <int DT, bool TRAIN, bool LIST>
 __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) Ctl ctl;   // every mbarrier + the error word: addressed as base + constant
@@ -398,8 +448,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   const int K = p.K;
   const SmemLayout L = smem_layout(K, D);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nk = D / 16;                       // k-steps per product
+  const int ns = DT > 0 ? (DT > DSLICE ? DT / DSLICE : 1) : (int)L.ns;   // e_dim slices
+  const int ds = DT > 0 ? (DT > DSLICE ? DSLICE : DT) : (int)L.ds;        // columns per slice
+  const int nk = ds / 16;                      // k-steps per slice
   const int nchunks = (K + 255) / 256;         // accumulator chunks per tile
+  const bool resident = nchunks * ns <= 2;     // whole operand image fits the two ring slots
   const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   const int64_t total_chunks = my_tiles * nchunks;
 
@@ -425,45 +478,70 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   const uint32_t tmem_base = ctl.tmem_slot;
 
   if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
-      // codebook operand image: K <= 512 stays resident in the two ring slots; larger codebooks are
-      // streamed chunk by chunk (256 codes) for every row tile from L2
-      const bool resident = nchunks <= 2;
-      auto load_chunk = [&](int c, int slot) {
-        const uint32_t bytes = (uint32_t)(((uint32_t)(D + 16) / 8u) * 256u * 16u);
-        const uint8_t* src = p.bimg + (size_t)c * bytes;
-        tc::mbar_arrive_expect_tx_a(BAR(B_B_FULL, slot), bytes);
-        for (uint32_t off = 0; off < bytes; off += 16384) {
-          const uint32_t n = min(16384u, bytes - off);
-          tc::bulk_g2s_a(smem0 + L.bimg + (uint32_t)slot * L.bchunk_bytes + off, src + off, n, BAR(B_B_FULL, slot));
-        }
-      };
-      if (resident) {
-        for (int c = 0; c < nchunks; ++c) load_chunk(c, c);
-      }
-      uint32_t qb = 0;   // running chunk counter of the streamed ring
-      STAT_DECL(1);
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        const int64_t tile = blockIdx.x + it * gridDim.x;
-        const int s = (int)(it & 1);
-        const uint32_t ph = (uint32_t)((it >> 1) & 1);
-        { STAT_T0(); wait_or_trap(BAR(B_STAGE_EMPTY, s), ph ^ 1u, err_out, ERR_STAGE_EMPTY); STAT_ADD(0); }
-        const int64_t row0 = tile * TM;
-        const int rows = (int)min((int64_t)TM, p.N - row0);
-        const uint32_t bytes = (uint32_t)rows * D * 4;
-        tc::mbar_arrive_expect_tx_a(BAR(B_STAGE_FULL, s), bytes);
-        if (TRAIN) tc::bulk_g2s_keep_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
-        else tc::bulk_g2s_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
-        if (!resident) {
-          for (int c = 0; c < nchunks; ++c, ++qb) {
-            const int slot = (int)(qb & 1u);
-            wait_or_trap(BAR(B_B_EMPTY, slot), ((qb >> 1) & 1u) ^ 1u, err_out, ERR_B_FULL);
-            load_chunk(c, slot);
+    // ===================== producer: z tile (slices) -> staging ring =====================
+    {
+      if (lane == 0 && resident) {
+        // the operand image stays in the two ring slots for the life of the CTA
+        for (int b = 0; b < nchunks * ns; ++b) {
+          const uint8_t* src = p.bimg + (size_t)b * L.bchunk_bytes;
+          tc::mbar_arrive_expect_tx_a(BAR(B_B_FULL, b), L.bchunk_bytes);
+          for (uint32_t off = 0; off < L.bchunk_bytes; off += 16384) {
+            const uint32_t n = min(16384u, L.bchunk_bytes - off);
+            tc::bulk_g2s_a(smem0 + L.bimg + (uint32_t)b * L.bchunk_bytes + off, src + off, n, BAR(B_B_FULL, b));
           }
         }
       }
+      uint32_t js = 0;   // running slice counter of the staging ring
+      STAT_DECL(1);
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t tile = blockIdx.x + it * gridDim.x;
+        const int64_t row0 = tile * TM;
+        const int rows = (int)min((int64_t)TM, p.N - row0);
+        for (int sl = 0; sl < ns; ++sl, ++js) {
+          const int s = (int)(js & 1u);
+          const uint32_t ph = (js >> 1) & 1u;
+          { STAT_T0(); wait_or_trap(BAR(B_STAGE_EMPTY, s), ph ^ 1u, err_out, ERR_STAGE_EMPTY); STAT_ADD(0); }
+          if (ns == 1) {
+            if (lane == 0) {   // the whole tile is one contiguous block
+              const uint32_t bytes = (uint32_t)rows * D * 4;
+              tc::mbar_arrive_expect_tx_a(BAR(B_STAGE_FULL, s), bytes);
+              if (TRAIN) tc::bulk_g2s_keep_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
+              else tc::bulk_g2s_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
+            }
+          } else {
+            // one bulk copy per row segment (ds * 4 bytes), issued by all lanes
+            if (lane == 0) tc::mbar_arrive_expect_tx_a(BAR(B_STAGE_FULL, s), (uint32_t)rows * ds * 4);
+            __syncwarp();
+            for (int r = lane; r < rows; r += 32) {
+              const float* src = p.z + (row0 + r) * D + sl * ds;
+              if (TRAIN) tc::bulk_g2s_keep_a(smem0 + L.stage[s] + (uint32_t)r * ds * 4, src, (uint32_t)ds * 4, BAR(B_STAGE_FULL, s));
+              else tc::bulk_g2s_a(smem0 + L.stage[s] + (uint32_t)r * ds * 4, src, (uint32_t)ds * 4, BAR(B_STAGE_FULL, s));
+            }
+          }
+          __syncwarp();
+        }
+      }
       STAT_FLUSH(1, 0);
+    }
+  } else if (warp == BLOAD_WARP) {
+    // ===================== codebook streamer: (chunk, slice) blocks of the operand image from L2 -> 2-slot ring =====================
+    if (lane == 0 && !resident) {
+      uint32_t qb = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        for (int c = 0; c < nchunks; ++c) {
+          for (int sl = 0; sl < ns; ++sl, ++qb) {
+            const uint32_t slot = qb & 1u;
+            wait_or_trap(BAR(B_B_EMPTY, slot), ((qb >> 1) & 1u) ^ 1u, err_out, ERR_B_FULL);
+            const uint32_t bytes = sl == ns - 1 ? L.bchunk_bytes : L.bslice_bytes;   // the fold columns ride with the last slice
+            const uint8_t* src = p.bimg + (size_t)(c * ns + sl) * L.bchunk_bytes;
+            tc::mbar_arrive_expect_tx_a(BAR(B_B_FULL, slot), bytes);
+            for (uint32_t off = 0; off < bytes; off += 16384) {
+              const uint32_t n = min(16384u, bytes - off);
+              tc::bulk_g2s_a(smem0 + L.bimg + slot * L.bchunk_bytes + off, src + off, n, BAR(B_B_FULL, slot));
+            }
+          }
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp; lane 0 issues) =====================
@@ -473,8 +551,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     // two TMEM stages and an epilogue that takes longer per chunk than the MMAs, the tensor pipe is
     // never the one waited for.
     {
-      const bool resident = nchunks <= 2;
-      if (resident) for (int c = 0; c < nchunks; ++c) wait_or_trap(BAR(B_B_FULL, c), 0, err_out, ERR_B_FULL);
+      if (resident) for (int b = 0; b < nchunks * ns; ++b) wait_or_trap(BAR(B_B_FULL, b), 0, err_out, ERR_B_FULL);
       const uint32_t b_lbo = 256u * 16u, b_sbo = 128;
       const uint32_t a_lbo = A_CHUNK_BYTES, a_sbo = 128;
       // descriptors are (address >> 4) in the low bits: advancing by one k-step (two 8-wide k-chunks)
@@ -487,14 +564,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const uint64_t a_desc1 = tc::make_smem_desc(sbase + L.a_img[1], a_lbo, a_sbo);
       const uint64_t b_desc0 = tc::make_smem_desc(sbase + L.bimg, b_lbo, b_sbo);
       const uint32_t barbase = tc::smem_u32(ctl.bars);
-      uint32_t q = 0;
+      uint32_t q = 0, qb = 0;   // accumulator chunks / operand blocks consumed so far
       STAT_DECL(3);
 #ifdef DVQ_TC_STATS
       const long long mma_t0 = clock64();
 #endif
       for (int64_t it = 0; it < my_tiles; ++it) {
-        const int a = (int)(it & 1);
-        { STAT_T0(); nb_sync(NB_A_FULL + a, NB_A_THREADS); STAT_ADD(0); }
+        const int a = L.a_bufs == 2 ? (int)(it & 1) : 0;
+        { STAT_T0(); nb_sync(NB_A_FULL + (int)(it & 1), NB_A_THREADS); STAT_ADD(0); }
         TRACE(0, 0, 0);
         for (int c = 0; c < nchunks; ++c, ++q) {
           const uint32_t t = q & 1u;
@@ -504,31 +581,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           const int n = min(256, K - c * 256);
           const uint32_t idesc = tc::make_idesc_f16(128, n, 0);
           const uint32_t d_tmem = tmem_base + t * 256u;
-          const uint32_t bslot = resident ? (uint32_t)c : (q & 1u);
-          if (!resident) wait_or_trap(BAR(B_B_FULL, bslot), (q >> 1) & 1u, err_out, ERR_B_FULL);
-          if (tc::elect_one()) {
-            const uint64_t bc = b_desc0 + (uint64_t)((bslot * L.bchunk_bytes) >> 4);
-            uint64_t ad = a ? a_desc1 : a_desc0, bd = bc;
-            uint32_t acc = 0;
+          for (int sl = 0; sl < ns; ++sl, ++qb) {
+            const uint32_t bslot = resident ? (uint32_t)(c * ns + sl) : (qb & 1u);
+            if (!resident) wait_or_trap(BAR(B_B_FULL, bslot), (qb >> 1) & 1u, err_out, ERR_B_FULL);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+              const uint64_t bc = b_desc0 + (uint64_t)((bslot * L.bchunk_bytes) >> 4);
+              uint64_t ad = (a ? a_desc1 : a_desc0) + (uint64_t)(sl * nk) * a_step, bd = bc;
+              uint32_t acc = sl > 0 ? 1u : 0u;
 #pragma unroll
-            for (int j = 0; j < nk; ++j) {   // zh . eh
-              tc::umma_f16(d_tmem, ad, bd, idesc, acc);
-              acc = 1; ad += a_step; bd += b_step;
-            }
-            if (USE_ZL) {
-              bd = bc;
-#pragma unroll
-              for (int j = 0; j < nk; ++j) {   // zl . eh  (A holds -zl: negate-A bit 13 of the descriptor)
-                tc::umma_f16(d_tmem, ad, bd, idesc | (1u << 13), 1);
-                ad += a_step; bd += b_step;
+              for (int j = 0; j < nk; ++j) {   // zh . eh, one slice
+                tc::umma_f16(d_tmem, ad, bd, idesc, acc);
+                acc = 1; ad += a_step; bd += b_step;
               }
+              if (USE_ZL) {   // single-slice shapes only (see vq_tc_supported)
+                bd = bc;
+#pragma unroll
+                for (int j = 0; j < nk; ++j) {   // zl . eh  (A holds -zl: negate-A bit 13 of the descriptor)
+                  tc::umma_f16(d_tmem, ad, bd, idesc | (1u << 13), 1);
+                  ad += a_step; bd += b_step;
+                }
+              }
+              if (sl == ns - 1) {
+                tc::umma_f16(d_tmem, ad, bd, idesc, 1);   // fold columns: they follow the last slice in A and in the ring slot
+                tc::umma_commit_a(barbase + 8u * (B_ACC_FULL + t));
+                if (c == nchunks - 1) tc::umma_commit_a(barbase + 8u * (uint32_t)(B_A_EMPTY + a));  // every MMA of this tile done: A image free
+              }
+              if (!resident) tc::umma_commit_a(barbase + 8u * (B_B_EMPTY + bslot));   // ring slot free once these MMAs have read it
             }
-            tc::umma_f16(d_tmem, ad, bd, idesc, 1);   // fold columns
-            tc::umma_commit_a(barbase + 8u * (B_ACC_FULL + t));
-            if (!resident) tc::umma_commit_a(barbase + 8u * (B_B_EMPTY + bslot));   // ring slot free once these MMAs have read it
-            if (c == nchunks - 1) tc::umma_commit_a(barbase + 8u * (uint32_t)(B_A_EMPTY + a));  // every MMA of this tile done: A image free
+            __syncwarp();
           }
-          __syncwarp();
           TRACE(0, 2, c & 1);
           wait_or_trap(BAR(B_ACC_FULL, t), (q >> 1) & 1u, err_out, ERR_ACC_FULL);
           TRACE(0, 3, c & 1);
@@ -546,32 +628,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     // ===================== converters: thread <-> tile row =====================
     const int r = (warp - CONV_WARP0) * 32 + lane;
     const CbMeta cb = *p.cb;
-    const int nv = D / 4;   // float4 per row
     STAT_DECL(3);
 #ifdef DVQ_TC_STATS
     const long long conv_t0 = clock64();
 #endif
+    const int nvs = ds / 4;   // float4 per row of one slice
+    uint32_t js = 0;          // running slice counter of the staging ring
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
-      const int s = (int)(it & 1), a = (int)(it & 1);
-      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      const int a = L.a_bufs == 2 ? (int)(it & 1) : 0;
+      const uint32_t aph = L.a_bufs == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);   // phase of B_A_EMPTY[a] this tile waits past
       const int rows = (int)min((int64_t)TM, p.N - tile * TM);
-      { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), ph, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
-      if (warp == CONV_WARP0) TRACE(3, 0, 0);
-      const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nv;
-      // pass 1: squared norm (lane-rotated chunk order: conflict-free 128-bit reads)
+      // squared norm of the row: from the staged tile (single slice, lane-rotated conflict-free 128-bit reads)
+      // or from the pre-pass (sliced e_dim: the scale is needed before the first slice is converted)
       float nsq = 0.f;
       bool finite = true;
-      if (r < rows) {
-        for (int i = 0; i < nv; ++i) {
-          const int c4 = (i + lane) & (nv - 1);
-          const float4 v = src[c4];
-          nsq = fmaf(v.x, v.x, nsq); nsq = fmaf(v.y, v.y, nsq); nsq = fmaf(v.z, v.z, nsq); nsq = fmaf(v.w, v.w, nsq);
+      if (ns == 1) {
+        const int s = (int)(js & 1u);
+        { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), (js >> 1) & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
+        if (warp == CONV_WARP0) TRACE(3, 0, 0);
+        const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nvs;
+        if (r < rows) {
+          for (int i = 0; i < nvs; ++i) {
+            const int c4 = (i + lane) & (nvs - 1);
+            const float4 v = src[c4];
+            nsq = fmaf(v.x, v.x, nsq); nsq = fmaf(v.y, v.y, nsq); nsq = fmaf(v.z, v.z, nsq); nsq = fmaf(v.w, v.w, nsq);
+          }
         }
-        finite = (nsq < 1e30f);   // false for inf / nan too
+      } else if (r < rows) {
+        nsq = __ldg(p.row_nsq + tile * TM + r);
       }
+      if (r < rows) finite = (nsq < 1e30f);   // false for inf / nan too
       // scales and bounds
-      const float zn = sqrtf(nsq) * (1.f + 1e-6f);
+      const float zn = sqrtf(nsq) * (1.f + 1e-4f);
       const bool tiny = !(nsq > 1e-30f);
       int ex = (int)((__float_as_uint(zn) >> 23) & 255u) - 127;         // zn in [2^ex, 2^(ex+1))
       float s_n = exp2f((float)(10 - ex));                              // s_n*zn in [2^10, 2^11)
@@ -583,51 +672,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const float fr = (s_n == 0.f) ? 0.f : exp2f((float)rexp);
       const float bias2 = 2.f * f0a * cb.b0;
       float eps = zs * cb.delta_max * (1.f + 1.f / 64.f)
-                + bias2 * ((float)((USE_ZL ? 2 : 1) * nk + 3) * (1.f / 1048576.f))      // tensor-core FP32 accumulation
-                + 16.f * fr * (1.f / 256.f);                                            // ee rounding (r_n = fr / 256)
+                + bias2 * ((float)((USE_ZL ? 2 : 1) * ns * nk + 3) * (1.f / 1048576.f))   // tensor-core FP32 accumulation
+                + 16.f * fr * (1.f / 256.f);                                              // ee rounding (r_n = fr / 256)
       if (USE_ZL) eps += (zs * (1.f / 4194304.f) + sqrtf((float)D) * (1.f / 33554432.f)) * cb.eh_norm_bound;   // zl rounding
       float rsq = 0.f;   // !USE_ZL: exact squared norm of the residual z' - zh that the product drops
       if (warp == CONV_WARP0) TRACE(3, 1, 0);
-      { STAT_T0(); wait_or_trap(BAR(B_A_EMPTY, a), ph ^ 1u, err_out, ERR_A_EMPTY); STAT_ADD(1); }
+      { STAT_T0(); wait_or_trap(BAR(B_A_EMPTY, a), aph ^ 1u, err_out, ERR_A_EMPTY); STAT_ADD(1); }
       if (warp == CONV_WARP0) TRACE(3, 2, 0);
-      // pass 2: convert and write the A image
+      // convert slice by slice and write the A image
       uint8_t* aimg = smem + L.a_img[a] + (r >> 3) * 128 + (r & 7) * 16;
-      for (int i = 0; i < nv / 2; ++i) {
-        const int c8 = (i + lane) & (nv / 2 - 1);                       // 8-wide k-chunk
-        const float4 v0 = src[2 * c8], v1 = src[2 * c8 + 1];
-        const float x[8] = {v0.x * s_n, v0.y * s_n, v0.z * s_n, v0.w * s_n, v1.x * s_n, v1.y * s_n, v1.z * s_n, v1.w * s_n};
-        // hi = fp16(x); the second term is stored NEGATED, nl = fp16(hi - x) (one FHADD each, no unpack); the
-        // MMA issuer sets the A-negate bit of the instruction descriptor for the zl.eh products
-        __half2 hi[4], lo[4];
+      for (int sl = 0; sl < ns; ++sl, ++js) {
+        const int s = (int)(js & 1u);
+        if (ns > 1) { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), (js >> 1) & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
+        const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nvs;
+        uint8_t* aslice = aimg + (size_t)(sl * (nvs / 2)) * A_CHUNK_BYTES;
+        for (int i = 0; i < nvs / 2; ++i) {
+          const int c8 = (i + lane) & (nvs / 2 - 1);                       // 8-wide k-chunk
+          const float4 v0 = src[2 * c8], v1 = src[2 * c8 + 1];
+          const float x[8] = {v0.x * s_n, v0.y * s_n, v0.z * s_n, v0.w * s_n, v1.x * s_n, v1.y * s_n, v1.z * s_n, v1.w * s_n};
+          // hi = fp16(x); with USE_ZL the second term is stored NEGATED, nl = fp16(hi - x) (one FHADD each, no
+          // unpack) and the MMA issuer sets the A-negate bit of the instruction descriptor for the zl.eh products
+          __half2 hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          hi[e] = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
-          const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi[e]);
-          const float r0 = half_minus_float(hb & 0xffffu, x[2 * e]), r1 = half_minus_float(hb >> 16, x[2 * e + 1]);   // exact
-          if (USE_ZL) lo[e] = __floats2half2_rn(r0, r1);
-          else rsq = fmaf(r1, r1, fmaf(r0, r0, rsq));
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi[e]);
+            const float r0 = half_minus_float(hb & 0xffffu, x[2 * e]), r1 = half_minus_float(hb >> 16, x[2 * e + 1]);   // exact
+            if (USE_ZL) lo[e] = __floats2half2_rn(r0, r1);
+            else rsq = fmaf(r1, r1, fmaf(r0, r0, rsq));
+          }
+          *reinterpret_cast<uint4*>(aslice + (size_t)c8 * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(hi);
+          if (USE_ZL) *reinterpret_cast<uint4*>(aslice + (size_t)(nvs / 2 + c8) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(lo);
         }
-        *reinterpret_cast<uint4*>(aimg + (size_t)c8 * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(hi);
-        if (USE_ZL) *reinterpret_cast<uint4*>(aimg + (size_t)(nv / 2 + c8) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(lo);
+        warp_arrive(BAR(B_STAGE_EMPTY, s));       // staging slot may be refilled
       }
       if (!USE_ZL) eps += sqrtf(rsq) * (1.f + 1e-4f) * cb.eh_norm_bound;
       float band = 2.f * eps * (1.f + 1.f / 16.f);
       if (degenerate) band = -1.f;    // marks "send to the exact kernel"
-      constexpr int kFold = USE_ZL ? 2 : 1;   // fold k-chunks follow the zh (and zl) chunks
+      const int kfold = (USE_ZL ? 2 : 1) * ns * (nvs / 2);   // fold k-chunks follow the zh (and zl) chunks
       {
         __half2 f[4];
         f[0] = __floats2half2_rn(f0a, fr);
         f[1] = __floats2half2_rn(fr, fr);
         f[2] = __floats2half2_rn(0.f, 0.f);
         f[3] = f[2];
-        *reinterpret_cast<uint4*>(aimg + (size_t)(kFold * nv / 2) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
+        *reinterpret_cast<uint4*>(aimg + (size_t)kfold * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
         f[0] = f[2]; f[1] = f[2];
-        *reinterpret_cast<uint4*>(aimg + (size_t)(kFold * nv / 2 + 1) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
+        *reinterpret_cast<uint4*>(aimg + (size_t)(kfold + 1) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(f);
       }
       reinterpret_cast<float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r] = band;
-      warp_arrive(BAR(B_STAGE_EMPTY, s));       // staging slot may be refilled
       tc::fence_proxy_async_smem();           // A image visible to the tensor core (async proxy)
-      nb_arrive(NB_A_FULL + a, NB_A_THREADS);
+      nb_arrive(NB_A_FULL + (int)(it & 1), NB_A_THREADS);
       if (warp == CONV_WARP0) TRACE(3, 3, 0);
     }
 #ifdef DVQ_TC_STATS
@@ -678,7 +773,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           uint32_t v[32];
           tc::tmem_ld32(tbase + (uint32_t)sc * 32u, v);
           tmem_ld_wait_dep(v);
-          filter_subchunk(v, c * 256 + sc * 32, 1u << ((c * 8 + sc) >> p.cand_gshift), band, st);
+          filter_subchunk<LIST>(v, c * 256 + sc * 32, LIST ? (uint32_t)(c * 8 + sc + 1) : 1u << ((c * 8 + sc) >> p.cand_gshift), band, st);
         }
         tc::tc_fence_before();
         if (w == 0) TRACE(1, 1, c & 1);
@@ -715,16 +810,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           const uint32_t cando = reinterpret_cast<const uint32_t*>(fin_key + 3 * TM)[r];
           if (ko < m1) {
             flag = (m1 - ko <= band);
-            cand = flag ? (cand | cando) : cando;      // an improvement beyond the band voids the old candidates
+            cand = flag ? cand_union<LIST>(cand, cando) : cando;      // an improvement beyond the band voids the old candidates
             m1 = ko; col = co; cnt = no;
           } else if (ko - m1 <= band) {
             flag = true;
-            cand |= cando;
+            cand = cand_union<LIST>(cand, cando);
           }
         }
         if (it + 1 < my_tiles) nb_arrive(NB_FIN_EMPTY, NB_FIN_THREADS);
         flag = flag || (cnt > 0);
-        if (band < 0.f) { flag = true; cand = 0x7fffffffu; }   // degenerate row: every group is a candidate
+        if (band < 0.f) { flag = true; cand = LIST ? CAND_OVERFLOW : 0x7fffffffu; }   // degenerate row: every code is a candidate
         const bool valid = r < rows;
         flag = flag && valid;
         if (it >= 2) { STAT_T0(); nb_sync(NB_SIDX_EMPTY + slot, NB_SIDX_THREADS); STAT_ADD(3); }
@@ -780,18 +875,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       if (gw == 0) TRACE(4, 0, 0);
       const int* sp = reinterpret_cast<const int*>(smem + L.sidx) + slot * TM + rbase;
       {
-        // undecided rows of this warp's 32 rows -> list for the exact FP32 kernel (one atomic per warp that has any)
+        // undecided rows of this warp's 32 rows -> list for the candidate refine kernel (one atomic per warp that
+        // has any).  LIST mode: rows with more than three candidate sub-chunks (and degenerate rows) go to a second
+        // list, stored downwards from the end of the same buffer, that the exact FP32 tile kernel re-evaluates
+        // against the whole codebook (a one-warp scan of a large codebook would take milliseconds).
         const int code = reinterpret_cast<const int*>(smem + L.sidx)[slot * TM + gw * rows_per_warp + lane];
         const bool und = code < 0 && lane < rows_per_warp && gw * rows_per_warp + lane < rows;
-        const unsigned bal = __ballot_sync(0xffffffffu, und);
+        const bool ovf = LIST && und && ((uint32_t)code & CAND_OVERFLOW) == CAND_OVERFLOW;
+        const unsigned bal = __ballot_sync(0xffffffffu, und && !ovf);
         if (bal) {
           int base = 0;
           if (lane == 0) base = atomicAdd(p.counters, __popc(bal));
           base = __shfl_sync(0xffffffffu, base, 0);
-          if (und) {
+          if (und && !ovf) {
             const int pos = base + __popc(bal & ((1u << lane) - 1u));
             p.row_list[pos] = (int)(row0 + gw * rows_per_warp + lane);
             p.cand_list[pos] = code & 0x7fffffff;
+          }
+        }
+        if (LIST) {
+          const unsigned bal2 = __ballot_sync(0xffffffffu, ovf);
+          if (bal2) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(p.counters + 2, __popc(bal2));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (ovf) p.row_list[p.N - 1 - (base + __popc(bal2 & ((1u << lane) - 1u)))] = (int)(row0 + gw * rows_per_warp + lane);
           }
         }
       }
@@ -881,23 +989,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 
 bool vq_tc_supported(int64_t N, int K, int D) {
   if (N <= 0 || N > 2147483647LL - 256) return false;
-  if (D < 16 || D > 256 || (D & (D - 1)) != 0) return false;   // power of two: index math is masks/shifts
+  if (D < 16 || D > 1024 || (D & (D - 1)) != 0) return false;   // power of two: index math is masks/shifts
+  if (USE_ZL && D > DSLICE) return false;
   if (K % 32 != 0 || K < 32 || K > 32768) return false;
-  return smem_layout(K, D).total + 128 + 512 <= 227 * 1024;   // + alignment slack + static barriers
+  return smem_layout(K, D).total <= SMEM_LIMIT;   // e_dim <= 256 with the current ring sizes
 }
 
 int vq_tc_cand_gshift(int K) {   // 31 candidate bits (bit 31 is the "undecided" flag of the hand-off word) cover K/32 sub-chunks in groups of 2^gshift
+  if (K > 992 && K <= 32704) return -1;   // list mode: up to three exact sub-chunk indices instead of a coarse mask
   int g = 0;
   while (((K + 31) / 32 + (1 << g) - 1) >> g > 31) ++g;
   return g;
 }
 
 size_t vq_tc_operand_bytes(int K, int D) {
-  return align_up(sizeof(CbMeta), 256) + align_up((size_t)((K + 255) / 256) * smem_layout(K, D).bchunk_bytes, 256);
+  const SmemLayout L = smem_layout(K, D);
+  return align_up(sizeof(CbMeta), 256) + align_up((size_t)((K + 255) / 256) * L.ns * L.bchunk_bytes, 256);
 }
 
+size_t vq_tc_rownorm_bytes(int64_t N, int D) { return D > DSLICE ? align_up(sizeof(float) * (size_t)N, 256) : 0; }
+
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,
-                 int64_t* idx, unsigned long long* hist, double* sse, void* bop, int* counters, int* row_list,
+                 int64_t* idx, unsigned long long* hist, double* sse, void* bop, float* row_nsq, int* counters, int* row_list,
                  int* cand_list, cudaStream_t s) {
   DeviceProps dp;
   int rc = device_props(&dp);
@@ -909,27 +1022,36 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   const SmemLayout L = smem_layout(K, D);
   tc_cb_stats_kernel<<<1, 256, 0, s>>>(ee, K, cb, counters);
   DVQ_CUDA_CHECK(cudaGetLastError());
-  DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, (size_t)((K + 255) / 256) * L.bchunk_bytes, s));
+  DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, (size_t)((K + 255) / 256) * L.ns * L.bchunk_bytes, s));
   tc_cb_image_kernel<<<(K * 32 + 255) / 256, 256, 0, s>>>(E, ee, K, D, cb, bimg);
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch(2);
+  if (D > DSLICE) {
+    if (!row_nsq) return fail(DVQ_ERR_WORKSPACE, "tcgen05 path with e_dim > 64 needs the row-norm workspace");
+    tc_row_nsq_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, s>>>(z, N, D, row_nsq);
+    DVQ_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
 
   TcParams p;
-  p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.N = N; p.K = K; p.D = D; p.train = train;
+  p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.row_nsq = row_nsq; p.N = N; p.K = K; p.D = D; p.train = train;
   p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list; p.cand_list = cand_list; p.cand_gshift = vq_tc_cand_gshift(K);
   p.stats = reinterpret_cast<unsigned long long*>(counters + 8);
   p.ntiles = (N + TM - 1) / TM;
   const size_t smem = L.total + 128;
   const int64_t grid = p.ntiles < dp.sm_count ? p.ntiles : dp.sm_count;
-#define DVQ_LAUNCH_TC(DT_, TR_)                                                                                         \
+#define DVQ_LAUNCH_TC(DT_, TR_, LS_)                                                                                         \
   do {                                                                                                                 \
-    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<DT_, TR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    vq_tc_kernel<DT_, TR_><<<(unsigned)grid, NTHREADS, smem, s>>>(p);                                                  \
+    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<DT_, TR_, LS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    vq_tc_kernel<DT_, TR_, LS_><<<(unsigned)grid, NTHREADS, smem, s>>>(p);                                                  \
   } while (0)
-  if (D == 64) {
-    if (train) DVQ_LAUNCH_TC(64, true); else DVQ_LAUNCH_TC(64, false);
+  const bool list = p.cand_gshift < 0;
+  if (D == 64 && !list) {
+    if (train) DVQ_LAUNCH_TC(64, true, false); else DVQ_LAUNCH_TC(64, false, false);
+  } else if (!list) {
+    if (train) DVQ_LAUNCH_TC(0, true, false); else DVQ_LAUNCH_TC(0, false, false);
   } else {
-    if (train) DVQ_LAUNCH_TC(0, true); else DVQ_LAUNCH_TC(0, false);
+    if (train) DVQ_LAUNCH_TC(0, true, true); else DVQ_LAUNCH_TC(0, false, true);
   }
 #undef DVQ_LAUNCH_TC
   DVQ_CUDA_CHECK(cudaGetLastError());

@@ -232,11 +232,14 @@ def test_host_buffer_entry_equals_device_entry(train):
     hq.close()
 
 
-@pytest.mark.parametrize("K,D", [(800, 64), (4096, 64), (1536, 32), (16384, 64)])
+@pytest.mark.parametrize("K,D", [(800, 64), (4096, 64), (1536, 32), (16384, 64),
+                                 (512, 128), (128, 256), (2048, 128), (4096, 256), (992, 128), (1024, 256)])
 @pytest.mark.parametrize("variant", ["default", "variant_b"])
 def test_streamed_codebook_tc_path(K, D, variant):
-    """Codebooks larger than the shared-memory-resident limit are streamed chunk by chunk through the
-    tcgen05 kernel: parity against the all-FP32 kernel and the oracle (band rule), ragged N."""
+    """Codebooks larger than the shared-memory-resident limit are streamed block by block through the
+    tcgen05 kernel, e_dim > 64 is contracted in 64-column slices (BASELINE config 4 shapes and the real
+    model's K = 128, D = 256 codebooks), K > 992 records candidates as sub-chunk lists: parity against the
+    all-FP32 kernel and the oracle (band rule), ragged N."""
     from dvq import _cabi
     N = 20000 + 37
     if variant == "default":
@@ -263,3 +266,30 @@ def test_streamed_codebook_tc_path(K, D, variant):
     assert rel_err(lt.item(), ls.item()) < REL
     if n_mis == 0:
         assert rel_err(pt.item(), ps.item()) < REL
+
+
+@pytest.mark.parametrize("K,D", [(512, 64), (2048, 64), (2048, 128)])
+def test_degenerate_rows_and_duplicate_codes_take_the_exact_path(K, D):
+    """Zero rows, huge rows and a codebook whose second half duplicates the first (every row has an exact
+    tie, K/2 .. many candidates) must come out exactly as the all-FP32 kernel gives them: the filter routes
+    them to the refine lists (mask mode at K = 512, sub-chunk lists + the overflow list above K = 992)."""
+    from dvq import _cabi
+    N = 3000 + 11
+    rng = np.random.default_rng(5)
+    half = (rng.standard_normal((K // 2, D)) * 0.05).astype(np.float32)
+    E = np.concatenate([half, half], axis=0)
+    z = rng.standard_normal((N, D)).astype(np.float32)
+    z[::97] = 0.0                      # zero rows
+    z[5::101] *= 1e18                  # outside the FP16 fold range
+    z[7::103] = half[rng.integers(0, K // 2, size=len(z[7::103]))]   # exactly on a (duplicated) code
+    out = {}
+    for name, path in (("simt", _cabi.DVQ_PATH_SIMT), ("tc", _cabi.DVQ_PATH_TC)):
+        m = _module(E, 1.0, 0.25, path)
+        m.onehot_limit_bytes = 0
+        with torch.no_grad():
+            idx, zq = m(torch.from_numpy(z).cuda(), False)
+        out[name] = (idx.cpu().numpy().reshape(-1), zq.cpu().numpy())
+        assert m.last_counters(N)[1] == 0
+    assert int(out["tc"][0].max()) < K // 2          # ties -> lowest index, as torch.argmin
+    assert np.array_equal(out["tc"][0], out["simt"][0])
+    assert np.array_equal(out["tc"][1].view(np.uint32), out["simt"][1].view(np.uint32))
