@@ -259,7 +259,7 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
 
 }  // namespace
 
-bool vq_refine_supported(int K, int D) { return (D == 16 || D == 32 || D == 64 || D == 128 || D == 256) && K >= 32; }
+bool vq_refine_supported(int K, int D) { return (D == 16 || D == 32 || D == 64 || D == 128 || D == 256 || D == 512) && K >= 32; }
 
 template <int DT>
 static int launch_refine_dt(const float* z, const float* E, const float* ee, int K, int train, float* z_q, int64_t* idx,
@@ -295,7 +295,8 @@ int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int
     case 64: return launch_refine_dt<64>(z, E, ee, K, train, z_q, idx, hist, sse, row_list, cand_list, n_list, gshift, ovf_last, n_ovf, dp.sm_count, s);
     case 128: return launch_refine_dt<128>(z, E, ee, K, train, z_q, idx, hist, sse, row_list, cand_list, n_list, gshift, ovf_last, n_ovf, dp.sm_count, s);
     case 256: return launch_refine_dt<256>(z, E, ee, K, train, z_q, idx, hist, sse, row_list, cand_list, n_list, gshift, ovf_last, n_ovf, dp.sm_count, s);
-    default: return fail(DVQ_ERR_BAD_SHAPE, "candidate refine kernel is instantiated for e_dim 16..256 (powers of two) only");
+    case 512: return launch_refine_dt<512>(z, E, ee, K, train, z_q, idx, hist, sse, row_list, cand_list, n_list, gshift, ovf_last, n_ovf, dp.sm_count, s);
+    default: return fail(DVQ_ERR_BAD_SHAPE, "candidate refine kernel is instantiated for e_dim 16..512 (powers of two) only");
   }
 }
 

@@ -55,6 +55,9 @@ constexpr int GATHER_WARPS = 4;
 constexpr int BLOAD_WARP = GATHER_WARP0 + GATHER_WARPS;   // codebook streamer (active when the image is not resident)
 constexpr int NUM_WARPS = BLOAD_WARP + 1;
 constexpr int DSLICE = 64;                   // e_dim is contracted in slices of at most 64 columns
+// slice width: the whole row up to 64 columns, 64-column slices up to e_dim 256, 32-column slices for e_dim 512
+// (the resident A image of 128 x 528 halfs leaves room for only small staging / ring slots)
+__host__ __device__ inline int slice_width(int D) { return D <= DSLICE ? D : (D <= 256 ? DSLICE : 32); }
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int META_SLOTS = 4;
 // true: A row = [zh | zl | fold] (22-bit z, two products per code); false: A row = [zh | fold] and the exact norm
@@ -104,7 +107,7 @@ constexpr uint32_t SMEM_LIMIT = 227u * 1024u - 640u;   // dynamic shared memory 
 
 __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   SmemLayout L;
-  L.ds = (uint32_t)(D < DSLICE ? D : DSLICE);
+  L.ds = (uint32_t)slice_width(D);
   L.ns = (uint32_t)D / L.ds;
   const uint32_t kc_s = L.ds / 8, kc_a = (uint32_t)((USE_ZL ? 2 : 1) * D + 16) / 8;
   L.bslice_bytes = kc_s * 256u * 16u;
@@ -172,7 +175,7 @@ __global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, CbMeta* 
 // e_dim slice), each block laid out [d' / 8][k % 256][d' % 8] halfs exactly as its shared-memory ring slot;
 // the 16 fold columns (d >= D) follow the last slice of a chunk inside the same block
 __host__ __device__ inline size_t bimg_offset(int k, int d, int D) {
-  const int ds = D < DSLICE ? D : DSLICE, ns = D / ds;
+  const int ds = slice_width(D), ns = D / ds;
   const size_t block_bytes = (size_t)(ds / 8 + 2) * 256 * 16;
   const int sl = d < D ? d / ds : ns - 1;
   const int dd = d < D ? d - sl * ds : ds + (d - D);
@@ -989,10 +992,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 
 bool vq_tc_supported(int64_t N, int K, int D) {
   if (N <= 0 || N > 2147483647LL - 256) return false;
-  if (D < 16 || D > 1024 || (D & (D - 1)) != 0) return false;   // power of two: index math is masks/shifts
+  if (D < 16 || D > 512 || (D & (D - 1)) != 0) return false;   // power of two: index math is masks/shifts
   if (USE_ZL && D > DSLICE) return false;
   if (K % 32 != 0 || K < 32 || K > 32768) return false;
-  return smem_layout(K, D).total <= SMEM_LIMIT;   // e_dim <= 256 with the current ring sizes
+  return smem_layout(K, D).total <= SMEM_LIMIT;
 }
 
 int vq_tc_cand_gshift(int K) {   // 31 candidate bits (bit 31 is the "undecided" flag of the hand-off word) cover K/32 sub-chunks in groups of 2^gshift

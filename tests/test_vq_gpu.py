@@ -233,7 +233,7 @@ def test_host_buffer_entry_equals_device_entry(train):
 
 
 @pytest.mark.parametrize("K,D", [(800, 64), (4096, 64), (1536, 32), (16384, 64),
-                                 (512, 128), (128, 256), (2048, 128), (4096, 256), (992, 128), (1024, 256)])
+                                 (512, 128), (128, 256), (2048, 128), (4096, 256), (992, 128), (1024, 256), (512, 512), (2048, 512)])
 @pytest.mark.parametrize("variant", ["default", "variant_b"])
 def test_streamed_codebook_tc_path(K, D, variant):
     """Codebooks larger than the shared-memory-resident limit are streamed block by block through the
