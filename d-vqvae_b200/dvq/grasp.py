@@ -61,12 +61,14 @@ def uniform_prior(n_codes: int = 128, seed: int = 0):
     return prior
 
 
-def pixelcnn_prior(model):
-    """Adapter for a reference ``GatedPixelCNN``: sample the 3x3 grid conditioned on the object code and
-    read the six hand-part positions (gen_net.py:92-100)."""
+def pixelcnn_prior(model, n_valid=None):
+    """Adapter for a ``GatedPixelCNN`` (dvq.pixelcnn's row-cached sampler or the reference's): sample the 3x3
+    grid conditioned on the object code and read the six hand-part positions (gen_net.py:92-100).  ``n_valid``
+    (dvq sampler only) restricts the classes to the codebook size for random-init synthetic runs."""
     def prior(idx6, batch):
         grid = idx6.view(batch, 1, 1).repeat(1, 3, 3)
-        x = model.generate(grid, idx6.view(batch), shape=(3, 3), batch_size=batch)
+        kw = {} if n_valid is None else {"n_valid": n_valid}
+        x = model.generate(grid, idx6.view(batch), shape=(3, 3), batch_size=batch, **kw)
         return torch.stack([x[:, 0, 1], x[:, 0, 2], x[:, 1, 1], x[:, 1, 2], x[:, 2, 1], x[:, 2, 2]], dim=1)
     return prior
 

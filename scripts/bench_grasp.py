@@ -30,3 +30,47 @@ line = {"metric": "grasps_per_sec", "value": B / ms * 1e3, "unit": "grasps/s", "
 print(json.dumps(line))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(line, open(os.path.join(ROOT, "gpurun_out", "grasp.json"), "w"), indent=1)
+
+# ---- with the PixelCNN prior (gen_net.py:34: GatedPixelCNN(512, 512, 15)), random init, classes limited to the 128 codebook rows
+if os.environ.get("PIXELCNN", "1") == "1":
+    from dvq.pixelcnn import GatedPixelCNN
+    from dvq.grasp import pixelcnn_prior
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    pcnn = GatedPixelCNN(512, 512, 15).to(dev).eval()
+    label = torch.randint(0, 128, (B,), device=dev)
+    res = {}
+
+    def timed(fn, iters=3):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters): fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    @torch.no_grad()
+    def reference_style_generate():
+        # the reference algorithm (models.py:187-197) on the same module: one full forward per sampled position
+        x = torch.zeros((B, 3, 3), dtype=torch.int64, device=dev)
+        for i in range(3):
+            for j in range(3):
+                logits = pcnn(x, label)[:, :, i, j].clone()
+                logits[:, 128:] = float("-inf")
+                probs = F.softmax(logits, -1)
+                probs = probs / probs.sum()
+                x[:, i, j] = probs.multinomial(1).squeeze(-1)
+        return x
+
+    res["sampler_reference_style_ms"] = timed(reference_style_generate)          # cuDNN convs (TF32 by default)
+    for prec_p in ("fp32", "tf32"):
+        pcnn.precision = prec_p
+        res["sampler_row_cached_%s_ms" % prec_p] = timed(lambda: pcnn.generate(None, label, batch_size=B, n_valid=128))
+    pcnn.precision = "tf32"
+    net.prior = pixelcnn_prior(pcnn, n_valid=128)
+    ms2 = timed(lambda: net.gen(obj))
+    res.update({"metric": "grasps_per_sec", "value": B / ms2 * 1e3, "unit": "grasps/s", "ms_per_batch": ms2, "batch": B,
+                "prior": "GatedPixelCNN(512,512,15) row-cached sampler, tf32 GEMMs, random init, 128 valid classes",
+                "pointnet_precision": prec})
+    print(json.dumps(res))
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "grasp_pixelcnn.json"), "w"), indent=1)
