@@ -116,11 +116,14 @@ class GatedPixelCNN(nn.Module):
             if layer.mask_type == "A":
                 wv[:, :, -1] = 0
                 wh[:, :, :, -1] = 0
+            kh = k // 2 + 1
+            # one [d, taps * 2d] matrix per kernel row (column taps side by side): a grid row is multiplied once
+            # and the per-tap results are shift-added, so no im2col copy is ever made
+            wv_rows = [wv[:, :, a].permute(1, 2, 0).reshape(wv.shape[1], -1).contiguous() for a in range(kh)]   # [d, k*2d]
             packs.append(dict(
-                k=k, residual=layer.residual,
-                wv=wv.permute(2, 3, 1, 0).reshape(-1, wv.shape[0]).contiguous(),          # [(kh*kw*d), 2d], tap-major
-                bv=layer.vert_stack.bias.detach(),
-                wh=wh[:, :, 0].permute(2, 1, 0).reshape(-1, wh.shape[0]).contiguous(),    # [(kw2*d), 2d]
+                k=k, residual=layer.residual, mask_a=layer.mask_type == "A",
+                wv_rows=wv_rows, bv=layer.vert_stack.bias.detach(),
+                wh=wh[:, :, 0].permute(1, 2, 0).reshape(wh.shape[1], -1).contiguous(),     # [d, kh*2d]
                 bh=layer.horiz_stack.bias.detach(),
                 wvh=layer.vert_to_horiz.weight.detach()[:, :, 0, 0].t().contiguous(), bvh=layer.vert_to_horiz.bias.detach(),
                 wr=layer.horiz_resid.weight.detach()[:, :, 0, 0].t().contiguous(), br=layer.horiz_resid.bias.detach(),
@@ -147,23 +150,48 @@ class GatedPixelCNN(nn.Module):
     def _gate(x, d):
         return torch.tanh(x[..., :d]) * torch.sigmoid(x[..., d:])
 
-    def _vert_row(self, packs, xv, x, label, r):
-        """Vertical stack of grid row r for every layer from the cached rows above it: writes the gated
-        activations into ``xv[l + 1][:, r]`` and returns the pre-activations (the horizontal stack's input)."""
+    @staticmethod
+    def _shift_add(dst, y, taps, first_shift):
+        """dst[:, c] += sum_b y[:, c + first_shift + b, b] over the columns that exist.  y: [B, Win, taps, C]."""
+        wout, win = dst.shape[1], y.shape[1]
+        for t in range(taps):
+            sh = first_shift + t
+            lo, hi = max(0, -sh), min(wout, win - sh)
+            if hi > lo:
+                dst[:, lo:hi] += y[:, lo + sh:hi + sh, t]
+
+    def _above(self, packs, xv, r, cache):
+        """Contribution of the finished rows (< r) to the vertical pre-activations of row r, per layer: constant
+        while row r is being sampled."""
+        above = []
+        for l, pk in enumerate(packs):
+            k, half = pk["k"], pk["k"] // 2
+            src = xv[l]
+            B, _, W, d = src.shape
+            acc = pk["bv"].expand(B, W, -1).clone()
+            for a in range(half):                            # kernel rows above the current one
+                rr = r + a - half
+                if rr >= 0:
+                    y = (src[:, rr].reshape(B * W, d) @ pk["wv_rows"][a]).view(B, W, k, -1)
+                    self._shift_add(acc, y, k, -half)
+            above.append(acc)
+        cache["above"] = above
+
+    def _vert_row(self, packs, xv, x, label, r, cache):
+        """Vertical stack of grid row r for every layer: cached part of the rows above + the current-row taps
+        (mask-B layers).  Writes the gated activations into ``xv[l + 1][:, r]`` and returns the pre-activations
+        (the horizontal stack's input)."""
         B, H, W = x.shape
         d = self.dim
         xv[0][:, r] = self.embedding(x[:, r, :])             # [B, W, d]  (x_v == x_h at the input, models.py:167)
         pre = []
         for l, pk in enumerate(packs):
             k, half = pk["k"], pk["k"] // 2
-            src = xv[l]
-            rows = []
-            for a in range(half + 1):                        # rows r-half..r x columns c-half..c+half of the previous layer
-                rr = r + a - half
-                rows.append(src[:, rr] if rr >= 0 else torch.zeros_like(src[:, 0]))
-            patch = F.pad(torch.stack(rows, dim=1), (0, 0, half, half))          # [B, kh, W + 2*half, d]
-            cols = torch.stack([patch[:, :, c:c + k].reshape(B, -1) for c in range(W)], dim=1)   # [B, W, kh*k*d]
-            h_vert = cols @ pk["wv"] + pk["bv"]                                   # [B, W, 2d]
+            h_vert = cache["above"][l]
+            if not pk["mask_a"]:                             # the last kernel row (the current grid row) is masked in layer 0
+                y = (xv[l][:, r].reshape(B * W, d) @ pk["wv_rows"][half]).view(B, W, k, -1)
+                h_vert = h_vert.clone()
+                self._shift_add(h_vert, y, k, -half)
             xv[l + 1][:, r] = self._gate(h_vert + pk["cond"][label][:, None, :], d)
             pre.append(h_vert)
         return pre
@@ -179,22 +207,25 @@ class GatedPixelCNN(nn.Module):
         if "xv" not in cache:
             cache["xv"] = [x.new_zeros((B, H, W, d), dtype=self.embedding.weight.dtype) for _ in range(len(packs) + 1)]
         xv = cache["xv"]
-        if j == 0 and i > 0:
-            # row i-1 was last evaluated before its final column was sampled (the mask-B layers see the
-            # whole current row): refresh it once with the finished indices, then it never changes again
-            self._vert_row(packs, xv, x, label, i - 1)
-        pre = self._vert_row(packs, xv, x, label, i)
+        if j == 0:
+            if i > 0:
+                # row i-1 was last evaluated before its final column was sampled (the mask-B layers see the
+                # whole current row): refresh it once with the finished indices, then it never changes again
+                self._vert_row(packs, xv, x, label, i - 1, cache)
+            self._above(packs, xv, i, cache)
+        pre = self._vert_row(packs, xv, x, label, i, cache)
         xh = xv[0][:, i, : j + 1]                            # horizontal stack: row i, columns <= j
+        n = j + 1
         for l, pk in enumerate(packs):
             half = pk["k"] // 2
             kh = half + 1
             cond = pk["cond"][label]                         # [B, 2d]
-            hp = F.pad(xh, (0, 0, half, 0))                                       # [B, j+1+half, d]: taps at columns c-half..c
-            hcols = torch.stack([hp[:, c:c + kh].reshape(B, -1) for c in range(j + 1)], dim=1)   # [B, j+1, kh*d]
-            h_horiz = hcols @ pk["wh"] + pk["bh"]
-            v2h = pre[l][:, : j + 1] @ pk["wvh"] + pk["bvh"]
-            out = self._gate(v2h + h_horiz + cond[:, None, :], d)
-            res = out @ pk["wr"] + pk["br"]
+            taps = kh - 1 if pk["mask_a"] else kh            # layer 0: the current column is masked
+            h_horiz = (pre[l][:, :n].reshape(B * n, -1) @ pk["wvh"]).view(B, n, -1) + (pk["bvh"] + pk["bh"])   # v2h + biases
+            y = (xh.reshape(B * n, d) @ pk["wh"]).view(B, n, kh, -1)
+            self._shift_add(h_horiz, y, taps, -half)         # taps at columns c-half..c
+            out = self._gate(h_horiz + cond[:, None, :], d)
+            res = (out.reshape(B * n, d) @ pk["wr"]).view(B, n, d) + pk["br"]
             xh = res + xh if pk["residual"] else res
         hid = torch.relu(xh[:, j] @ head["w1"] + head["b1"])
         return hid @ head["w2"] + head["b2"]                                      # [B, input_dim]
