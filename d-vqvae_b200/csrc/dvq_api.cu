@@ -88,6 +88,8 @@ VqWorkspace vq_workspace_layout(int64_t N, int K, int D, int flags) {
   if (may_tc) off = align_up(off + vq_tc_operand_bytes(K, D), 1024);
   w.off_rowmeta = off;
   if (may_tc) off = align_up(off + vq_tc_rownorm_bytes(N, D), 256);
+  w.off_binned = off;
+  if (may_tc) off = align_up(off + vq_refine_binned_bytes(N), 256);
   w.total = off;
   return w;
 }
@@ -192,7 +194,8 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
       int* cand_list = reinterpret_cast<int*>(ws + w.off_rowlist + align_up(sizeof(int) * (size_t)N, 256));
       profile_mark(1, true, s);
       float* row_nsq = vq_tc_rownorm_bytes(N, D) ? reinterpret_cast<float*>(ws + w.off_rowmeta) : nullptr;
-      rc = launch_vq_tc(z, E, ee, N, K, D, train, z_q, idx, hist, sse, ws + w.off_bop, row_nsq, counters, row_list, cand_list, s);
+      rc = launch_vq_tc(z, E, ee, N, K, D, train, z_q, idx, hist, sse, ws + w.off_bop, row_nsq, counters, row_list, cand_list,
+                        reinterpret_cast<int*>(ws + w.off_binned), (int)(vq_refine_binned_zero_bytes() / sizeof(int)), s);
       profile_mark(1, false, s);
       if (rc) return rc;
       // exact FP32 refine of the rows the filter flagged (device-side count, no host sync): restricted to
@@ -202,8 +205,16 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
       //  list stored downwards from the end of the same buffer; both kernels re-evaluate them against every code)
       const bool list_mode = vq_tc_cand_gshift(K) < 0;
       if (vq_refine_supported(K, D)) {
-        rc = launch_vq_refine(z, E, ee, K, D, train, z_q, idx, hist, sse, row_list, cand_list, counters, vq_tc_cand_gshift(K),
-                              list_mode ? row_list + (N - 1) : nullptr, list_mode ? counters + 2 : nullptr, s);
+        // binned kernels first; the per-row kernel then takes whatever they handed back (normally nothing:
+        // counters[5] / counters[6] stay zero and it exits at once)
+        static const bool per_row_only = getenv("DVQ_REFINE_PER_ROW") != nullptr;   // A/B switch for measurements
+        if (!per_row_only)
+          rc = launch_vq_refine_binned(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, cand_list, counters, list_mode ? 1 : 0,
+                                       ws + w.off_binned, s);
+        if (!rc)
+          rc = launch_vq_refine(z, E, ee, K, D, train, z_q, idx, hist, sse, row_list, cand_list, per_row_only ? counters : counters + 5,
+                                vq_tc_cand_gshift(K), list_mode ? row_list + (N - 1) : nullptr,
+                                list_mode ? (per_row_only ? counters + 2 : counters + 6) : nullptr, s);
       } else {
         rc = launch_vq_simt(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, counters, 1, s);
         if (!rc && list_mode)

@@ -42,6 +42,7 @@ struct VqWorkspace {
   size_t off_rowlist;   // int   [2][N]         rows the tensor-core filter could not decide + their candidate masks
   size_t off_bop;       // operand image of the codebook for the tcgen05 path
   size_t off_rowmeta;   // float [N]            ||z_n||^2 for the sliced tcgen05 path (e_dim > 64), else empty
+  size_t off_binned;    // bin tables + (row, sub-chunk) pair list of the binned refine (vq_refine_binned.cu)
   size_t total;
 };
 VqWorkspace vq_workspace_layout(int64_t N, int K, int D, int flags);
@@ -62,7 +63,8 @@ size_t vq_tc_operand_bytes(int K, int D);
 size_t vq_tc_rownorm_bytes(int64_t N, int D);
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
                  float* z_q, int64_t* idx, unsigned long long* hist, double* sse,
-                 void* bop, float* row_nsq, int* counters, int* row_list, int* cand_list, cudaStream_t s);
+                 void* bop, float* row_nsq, int* counters, int* row_list, int* cand_list, int* zero_ints, int zero_n,
+                 cudaStream_t s);
 
 // candidate-restricted exact refine (vq_refine.cu); cand_list[i] = bit mask of 32*2^gshift-code groups
 bool vq_refine_supported(int K, int D);
@@ -70,6 +72,14 @@ int vq_tc_cand_gshift(int K);
 int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int D, int train, float* z_q, int64_t* idx,
                      unsigned long long* hist, double* sse, const int* row_list, const int* cand_list,
                      const int* n_list, int gshift, const int* ovf_last, const int* n_ovf, cudaStream_t s);
+
+// binned exact refine (vq_refine_binned.cu): (row, sub-chunk) pairs bucketed by sub-chunk; hands the list to
+// launch_vq_refine through counters[5] / counters[6] when the pairs do not fit its workspace
+size_t vq_refine_binned_bytes(int64_t N);
+size_t vq_refine_binned_zero_bytes();
+int launch_vq_refine_binned(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,
+                            int64_t* idx, unsigned long long* hist, double* sse, const int* row_list, const int* cand_list,
+                            int* counters, int list_mode, void* ws, cudaStream_t s);
 
 int launch_onehot(const int64_t* idx, int64_t N, int K, float* onehot, cudaStream_t s);
 int launch_finalize(const unsigned long long* hist, const double* sse, int64_t N, int K, int D, float al,

@@ -32,6 +32,8 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* zbuf = smem_f + warp * 2 * DT;             // double-buffered z row of this warp
   float* es = smem_f + NW * 2 * DT;
+  // nothing listed (the usual case when the binned kernels ran first): leave before staging the codebook
+  if (*n_list == 0 && (n_ovf == nullptr || *n_ovf == 0)) return;
   if (SMEM_E) {
     for (int i = tid; i < K * (DT / 4); i += RTHREADS) {
       const int k = i / (DT / 4), d = (i - k * (DT / 4)) * 4;

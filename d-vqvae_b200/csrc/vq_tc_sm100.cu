@@ -91,7 +91,7 @@ struct TcParams {
   int* counters;   // [0] refine-list length, [1] protocol error code
   int* row_list;
   int* cand_list;       // candidates of each listed row: group mask (bit g = codes [32*g<<gshift, ...)) or sub-chunk list
-  int cand_gshift;      // mask mode: log2 of the sub-chunks per mask bit; -1: list mode (see cand_union)
+  int cand_gshift;      // 0: mask mode (bit g = sub-chunk g); -1: list mode (see cand_union)
   unsigned long long* stats;   // optional wait-time accounting (DVQ_TC_STATS builds)
   int64_t ntiles;
 };
@@ -140,8 +140,10 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
 // ------------------------------------------------------------------------------------------------
 // codebook preparation (tiny): scale, FP16 operand image, exact rounding residual
 // ------------------------------------------------------------------------------------------------
-__global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, CbMeta* __restrict__ cb, int* __restrict__ counters) {
+__global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, CbMeta* __restrict__ cb, int* __restrict__ counters,
+                                   int* __restrict__ zero_ints, int zero_n) {
   __shared__ float red[32];
+  for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_ints[i] = 0;   // bin tables of the binned refine
   float m = 0.f;
   bool bad = false;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -383,6 +385,22 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
+// FADD2 / FMUL2: each half is an ordinary IEEE round-to-nearest FP32 operation (no contraction possible)
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 
 // One 32-column sub-chunk of raw accumulators (all >= 0, so float order == bit order):
 //   pass 1  FMNMX3 tree -> sub-chunk minimum -> running minimum with exact reset of the ambiguity state;
@@ -393,7 +411,7 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
 //           inside the band is the minimum itself), so no per-element index packing is needed.
 // ~3 issued instructions per element: 0.5 FMNMX3 (ALU) + 1 FFMA.SAT + 0.5 FFMA2 (FMA pipe).
 template <bool LIST>
-__device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uint32_t gbit, float band, RowState& st) {
+__device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uint32_t gbit, float band, float band_big, RowState& st) {
   const float BIG = 1048576.f;
   float key[32];
 #pragma unroll
@@ -404,15 +422,14 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
   float a6 = min3f(key[18], key[19], key[20]), a7 = min3f(key[21], key[22], key[23]);
   float a8 = min3f(key[24], key[25], key[26]), a9 = min3f(key[27], key[28], key[29]);
   a0 = min3f(a0, a1, a2); a3 = min3f(a3, a4, a5); a6 = min3f(a6, a7, a8); a9 = min3f(a9, key[30], key[31]);
-  const float m = fminf(min3f(a0, a3, a6), a9);
+  // running minimum folded into the tree: m1n = min(sub-chunk minimum, previous minimum)
+  const float m1n = min3f(min3f(a0, a3, a6), a9, st.m1);
   // An improvement by more than the band voids every earlier key exactly (cnt := -1 cancels the new
-  // minimum's own hit below); a smaller improvement leaves the old minimum inside the band, which the
-  // new minimum's own hit accounts for.
-  if (m < st.m1) {
-    if (st.m1 - m > band) { st.cnt = -1; st.cand = 0u; }
-    st.m1 = m;
-  }
-  const float TB = (st.m1 + band) * BIG;
+  // minimum's own hit below); a smaller improvement (or none: 0) leaves the old minimum inside the band,
+  // which the new minimum's own hit accounts for.
+  if (st.m1 - m1n > band) { st.cnt = -1; st.cand = 0u; }
+  st.m1 = m1n;
+  const float TB = fmaf(m1n, BIG, band_big);   // == (m1 + band) * 2^20: scaling by a power of two commutes with the rounding
   const uint64_t two = pack_f32x2(2.f, 2.f);
   // four independent Horner chains of 4 steps (columns 0-7, 8-15, 16-23, 24-31): short dependency chains
   uint64_t h0 = pack_f32x2(0.f, 0.f), h1 = h0, h2 = h0, h3 = h0;
@@ -428,6 +445,7 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
   const uint64_t acc2 = ffma2(ffma2(ffma2(h0, sixteen, h1), sixteen, h2), sixteen, h3);
   float fe, fo;
   unpack_f32x2(acc2, fe, fo);
+  // both masks in one integer: fe * 65536 + fo would need 32 mantissa bits, so the halves are converted separately
   const uint32_t bits = ((uint32_t)__float2int_rn(fe) << 16) | (uint32_t)__float2int_rn(fo);
   st.cnt += __popc(bits);
   if (bits) { st.cand = cand_union<LIST>(st.cand, gbit); st.bits = bits; st.col0 = col0; }   // the position is decoded once per row
@@ -652,11 +670,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         if (warp == CONV_WARP0) TRACE(3, 0, 0);
         const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nvs;
         if (r < rows) {
+          // two packed (FFMA2) accumulator pairs: half the issued instructions and four short dependency chains
+          uint64_t n01 = pack_f32x2(0.f, 0.f), n23 = n01;
           for (int i = 0; i < nvs; ++i) {
             const int c4 = (i + lane) & (nvs - 1);
             const float4 v = src[c4];
-            nsq = fmaf(v.x, v.x, nsq); nsq = fmaf(v.y, v.y, nsq); nsq = fmaf(v.z, v.z, nsq); nsq = fmaf(v.w, v.w, nsq);
+            const uint64_t v01 = pack_f32x2(v.x, v.y), v23 = pack_f32x2(v.z, v.w);
+            n01 = ffma2(v01, v01, n01); n23 = ffma2(v23, v23, n23);
           }
+          float q0, q1, q2, q3;
+          unpack_f32x2(n01, q0, q1); unpack_f32x2(n23, q2, q3);
+          nsq = (q0 + q1) + (q2 + q3);
         }
       } else if (r < rows) {
         nsq = __ldg(p.row_nsq + tile * TM + r);
@@ -678,7 +702,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
                 + bias2 * ((float)((USE_ZL ? 2 : 1) * ns * nk + 3) * (1.f / 1048576.f))   // tensor-core FP32 accumulation
                 + 16.f * fr * (1.f / 256.f);                                              // ee rounding (r_n = fr / 256)
       if (USE_ZL) eps += (zs * (1.f / 4194304.f) + sqrtf((float)D) * (1.f / 33554432.f)) * cb.eh_norm_bound;   // zl rounding
-      float rsq = 0.f;   // !USE_ZL: exact squared norm of the residual z' - zh that the product drops
+      uint64_t rsq2 = pack_f32x2(0.f, 0.f);   // !USE_ZL: exact squared norm of the residual z' - zh that the product drops (even / odd partial sums)
+      const uint64_t s_n2 = pack_f32x2(s_n, s_n);
       if (warp == CONV_WARP0) TRACE(3, 1, 0);
       { STAT_T0(); wait_or_trap(BAR(B_A_EMPTY, a), aph ^ 1u, err_out, ERR_A_EMPTY); STAT_ADD(1); }
       if (warp == CONV_WARP0) TRACE(3, 2, 0);
@@ -692,24 +717,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         for (int i = 0; i < nvs / 2; ++i) {
           const int c8 = (i + lane) & (nvs / 2 - 1);                       // 8-wide k-chunk
           const float4 v0 = src[2 * c8], v1 = src[2 * c8 + 1];
-          const float x[8] = {v0.x * s_n, v0.y * s_n, v0.z * s_n, v0.w * s_n, v1.x * s_n, v1.y * s_n, v1.z * s_n, v1.w * s_n};
+          // scale by the power-of-two s_n, two elements per FMUL2 (exact)
+          const uint64_t xp[4] = {fmul2(pack_f32x2(v0.x, v0.y), s_n2), fmul2(pack_f32x2(v0.z, v0.w), s_n2),
+                                  fmul2(pack_f32x2(v1.x, v1.y), s_n2), fmul2(pack_f32x2(v1.z, v1.w), s_n2)};
           // hi = fp16(x); with USE_ZL the second term is stored NEGATED, nl = fp16(hi - x) (one FHADD each, no
           // unpack) and the MMA issuer sets the A-negate bit of the instruction descriptor for the zl.eh products
           __half2 hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            hi[e] = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+            float x0, x1;
+            unpack_f32x2(xp[e], x0, x1);
+            hi[e] = __floats2half2_rn(x0, x1);
             const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi[e]);
-            const float r0 = half_minus_float(hb & 0xffffu, x[2 * e]), r1 = half_minus_float(hb >> 16, x[2 * e + 1]);   // exact
+            const float r0 = half_minus_float(hb & 0xffffu, x0), r1 = half_minus_float(hb >> 16, x1);   // exact
             if (USE_ZL) lo[e] = __floats2half2_rn(r0, r1);
-            else rsq = fmaf(r1, r1, fmaf(r0, r0, rsq));
+            else { const uint64_t rp = pack_f32x2(r0, r1); rsq2 = ffma2(rp, rp, rsq2); }
           }
           *reinterpret_cast<uint4*>(aslice + (size_t)c8 * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(hi);
           if (USE_ZL) *reinterpret_cast<uint4*>(aslice + (size_t)(nvs / 2 + c8) * A_CHUNK_BYTES) = *reinterpret_cast<uint4*>(lo);
         }
         warp_arrive(BAR(B_STAGE_EMPTY, s));       // staging slot may be refilled
       }
-      if (!USE_ZL) eps += sqrtf(rsq) * (1.f + 1e-4f) * cb.eh_norm_bound;
+      if (!USE_ZL) {
+        float rs0, rs1;
+        unpack_f32x2(rsq2, rs0, rs1);
+        eps += sqrtf(rs0 + rs1) * (1.f + 1e-4f) * cb.eh_norm_bound;
+      }
       float band = 2.f * eps * (1.f + 1.f / 16.f);
       if (degenerate) band = -1.f;    // marks "send to the exact kernel"
       const int kfold = (USE_ZL ? 2 : 1) * ns * (nvs / 2);   // fold k-chunks follow the zh (and zl) chunks
@@ -752,7 +785,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int slot = (int)(it & 1);
       RowState st;
       st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0; st.bits = 0u; st.col0 = 0; st.cand = 0u;
-      float band = 0.f;
+      float band = 0.f, band_big = 0.f;
       for (int c = 0; c < nchunks; ++c, ++q) {
         const uint32_t t = q & 1u;
         {
@@ -764,19 +797,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         tc::tc_fence_after();
         if (w == 0) TRACE(1, 0, c & 1);
         if (w == 4) TRACE(2, 0, c & 1);
-        if (c == 0) band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
+        if (c == 0) {
+          band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
+          band_big = band * 1048576.f;
+        }
         const int n = min(256, K - c * 256);
         const uint32_t tbase = tmem_base + lane_addr + t * 256u;
         // my sub-chunks of this chunk: every EPQ-th one; the owner warp (wq == 0) takes the residue class
         // with the fewest members (it also merges, writes idx and the histogram).  The loop is kept rolled so the epilogue
         // stays inside the instruction cache; the TMEM load latency is covered by the other warps of
         // the sub-partition.
+        // (mask mode: one candidate bit per 32-code sub-chunk — K <= 992, see vq_tc_cand_gshift; list mode: sub-chunk index + 1)
+        const int sc0 = (wq + EPQ - 1) % EPQ;
+        int col = c * 256 + sc0 * 32;
+        const int col_end = c * 256 + n;
+        uint32_t taddr = tbase + (uint32_t)sc0 * 32u;
+        uint32_t gbit = LIST ? (uint32_t)(c * 8 + sc0 + 1) : 1u << (c * 8 + sc0);
 #pragma unroll 1
-        for (int sc = (wq + EPQ - 1) % EPQ; sc * 32 < n; sc += EPQ) {
+        for (; col < col_end; col += 32 * EPQ, taddr += 32u * EPQ, gbit = LIST ? gbit + EPQ : gbit << EPQ) {
           uint32_t v[32];
-          tc::tmem_ld32(tbase + (uint32_t)sc * 32u, v);
+          tc::tmem_ld32(taddr, v);
           tmem_ld_wait_dep(v);
-          filter_subchunk<LIST>(v, c * 256 + sc * 32, LIST ? (uint32_t)(c * 8 + sc + 1) : 1u << ((c * 8 + sc) >> p.cand_gshift), band, st);
+          filter_subchunk<LIST>(v, col, gbit, band, band_big, st);
         }
         tc::tc_fence_before();
         if (w == 0) TRACE(1, 1, c & 1);
@@ -931,11 +973,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
             for (int u = 0; u < U; ++u) {
               float4 o4 = e4[u];
               if (TRAIN) {
-                const float dx = __fsub_rn(e4[u].x, z4[u].x), dy = __fsub_rn(e4[u].y, z4[u].y);
-                const float dz = __fsub_rn(e4[u].z, z4[u].z), dw = __fsub_rn(e4[u].w, z4[u].w);
-                const float ss = fmaf(dw, dw, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-                lsse = fmaf(kk[u] < 0 ? 0.f : 1.f, ss, lsse);      // undecided rows are accounted by the exact kernel
-                o4 = make_float4(__fadd_rn(z4[u].x, dx), __fadd_rn(z4[u].y, dy), __fadd_rn(z4[u].z, dz), __fadd_rn(z4[u].w, dw));
+                // packed FP32 (FADD2 / FMUL2 / FFMA2): d = fl(e - z), z_q = fl(z + d), two elements per instruction,
+                // each half an ordinary IEEE operation (bit-identical to the scalar form, no contraction)
+                const uint64_t e01 = pack_f32x2(e4[u].x, e4[u].y), e23 = pack_f32x2(e4[u].z, e4[u].w);
+                const uint64_t z01 = pack_f32x2(z4[u].x, z4[u].y), z23 = pack_f32x2(z4[u].z, z4[u].w);
+                const uint64_t d01 = fsub2(e01, z01), d23 = fsub2(e23, z23);
+                const uint64_t s2 = ffma2(d23, d23, fmul2(d01, d01));
+                float s0, s1;
+                unpack_f32x2(s2, s0, s1);
+                lsse = fmaf(kk[u] < 0 ? 0.f : 1.f, s0 + s1, lsse);      // undecided rows are accounted by the exact kernel
+                unpack_f32x2(fadd2(z01, d01), o4.x, o4.y);
+                unpack_f32x2(fadd2(z23, d23), o4.z, o4.w);
               }
               __stcs(reinterpret_cast<float4*>(op + (int64_t)((t0 + u) * rps) * D), o4);   // streaming: never re-read
             }
@@ -994,15 +1042,12 @@ bool vq_tc_supported(int64_t N, int K, int D) {
   if (N <= 0 || N > 2147483647LL - 256) return false;
   if (D < 16 || D > 512 || (D & (D - 1)) != 0) return false;   // power of two: index math is masks/shifts
   if (USE_ZL && D > DSLICE) return false;
-  if (K % 32 != 0 || K < 32 || K > 32768) return false;
+  if (K % 32 != 0 || K < 32 || K > 32704) return false;   // list-mode candidate entries are 10 bits (sub-chunk index + 1 <= 1023)
   return smem_layout(K, D).total <= SMEM_LIMIT;
 }
 
-int vq_tc_cand_gshift(int K) {   // 31 candidate bits (bit 31 is the "undecided" flag of the hand-off word) cover K/32 sub-chunks in groups of 2^gshift
-  if (K > 992 && K <= 32704) return -1;   // list mode: up to three exact sub-chunk indices instead of a coarse mask
-  int g = 0;
-  while (((K + 31) / 32 + (1 << g) - 1) >> g > 31) ++g;
-  return g;
+int vq_tc_cand_gshift(int K) {   // 31 candidate bits (bit 31 is the "undecided" flag of the hand-off word), one per 32-code sub-chunk
+  return K <= 992 ? 0 : -1;      // -1 = list mode: up to three exact sub-chunk indices instead of a mask
 }
 
 size_t vq_tc_operand_bytes(int K, int D) {
@@ -1014,7 +1059,7 @@ size_t vq_tc_rownorm_bytes(int64_t N, int D) { return D > DSLICE ? align_up(size
 
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,
                  int64_t* idx, unsigned long long* hist, double* sse, void* bop, float* row_nsq, int* counters, int* row_list,
-                 int* cand_list, cudaStream_t s) {
+                 int* cand_list, int* zero_ints, int zero_n, cudaStream_t s) {
   DeviceProps dp;
   int rc = device_props(&dp);
   if (rc) return rc;
@@ -1023,7 +1068,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   CbMeta* cb = static_cast<CbMeta*>(bop);
   uint8_t* bimg = static_cast<uint8_t*>(bop) + align_up(sizeof(CbMeta), 256);
   const SmemLayout L = smem_layout(K, D);
-  tc_cb_stats_kernel<<<1, 256, 0, s>>>(ee, K, cb, counters);
+  tc_cb_stats_kernel<<<1, 256, 0, s>>>(ee, K, cb, counters, zero_ints, zero_n);
   DVQ_CUDA_CHECK(cudaGetLastError());
   DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, (size_t)((K + 255) / 256) * L.ns * L.bchunk_bytes, s));
   tc_cb_image_kernel<<<(K * 32 + 255) / 256, 256, 0, s>>>(E, ee, K, D, cb, bimg);
