@@ -48,6 +48,10 @@ int device_props(DeviceProps* out) {
 static long long g_launches = 0;
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 
+static int g_refine_mode = 0;            // dvq_vq_set_refine
+static long long g_refine_pair_cap = 0;
+long long refine_pair_cap_override() { return __atomic_load_n(&g_refine_pair_cap, __ATOMIC_RELAXED); }
+
 static const int kStages = 4;
 static const int kProfSlots = 128;  // event pairs per stage between enable and read-out
 static thread_local bool g_prof_on = false;
@@ -105,6 +109,13 @@ int dvq_abi_version(void) { return DVQ_ABI_VERSION; }
 const char* dvq_last_error(void) { return g_err; }
 
 long long dvq_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int dvq_vq_set_refine(int mode, long long pair_cap) {
+  if (mode < 0 || mode > 2) return fail(DVQ_ERR_BAD_ARG, "refine mode must be 0 (auto), 1 (per-row) or 2 (binned)");
+  __atomic_store_n(&g_refine_mode, mode, __ATOMIC_RELAXED);
+  __atomic_store_n(&g_refine_pair_cap, pair_cap > 0 ? pair_cap : 0, __ATOMIC_RELAXED);
+  return DVQ_OK;
+}
 
 int dvq_profile_enable(int on) {
   g_prof_on = on != 0;
@@ -205,9 +216,17 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
       //  list stored downwards from the end of the same buffer; both kernels re-evaluate them against every code)
       const bool list_mode = vq_tc_cand_gshift(K) < 0;
       if (vq_refine_supported(K, D)) {
-        // binned kernels first; the per-row kernel then takes whatever they handed back (normally nothing:
-        // counters[5] / counters[6] stay zero and it exits at once)
-        static const bool per_row_only = getenv("DVQ_REFINE_PER_ROW") != nullptr;   // A/B switch for measurements
+        // Two exact refine paths with identical results: the per-row kernel (one warp per undecided row) is the
+        // faster one while the FP32 codebook fits its shared memory (measured at K = 512, e_dim = 64: 0.105 vs
+        // 0.128 ms for 108 k rows); beyond that the binned kernels win by 2-5x (code rows register-resident per
+        // bucket instead of re-read from L2 per row).  The binned path hands its list back to the per-row kernel
+        // through counters[5] / counters[6] when the pairs do not fit its workspace (normally both stay zero and
+        // the per-row kernel exits at once).  dvq_vq_set_refine / DVQ_REFINE_PER_ROW / DVQ_REFINE_BINNED force one path.
+        static const bool env_per_row = getenv("DVQ_REFINE_PER_ROW") != nullptr;
+        static const bool env_binned = getenv("DVQ_REFINE_BINNED") != nullptr;
+        const int mode = __atomic_load_n(&g_refine_mode, __ATOMIC_RELAXED);
+        const bool force_per_row = env_per_row || mode == 1, force_binned = env_binned || mode == 2;
+        const bool per_row_only = force_per_row || (!force_binned && vq_refine_codebook_in_smem(K, D));
         if (!per_row_only)
           rc = launch_vq_refine_binned(z, E, ee, N, K, D, train, z_q, idx, hist, sse, row_list, cand_list, counters, list_mode ? 1 : 0,
                                        ws + w.off_binned, s);

@@ -68,6 +68,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
 
 // candidate-restricted exact refine (vq_refine.cu); cand_list[i] = bit mask of 32*2^gshift-code groups
 bool vq_refine_supported(int K, int D);
+bool vq_refine_codebook_in_smem(int K, int D);
 int vq_tc_cand_gshift(int K);
 int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int D, int train, float* z_q, int64_t* idx,
                      unsigned long long* hist, double* sse, const int* row_list, const int* cand_list,
@@ -75,6 +76,7 @@ int launch_vq_refine(const float* z, const float* E, const float* ee, int K, int
 
 // binned exact refine (vq_refine_binned.cu): (row, sub-chunk) pairs bucketed by sub-chunk; hands the list to
 // launch_vq_refine through counters[5] / counters[6] when the pairs do not fit its workspace
+long long refine_pair_cap_override();   // dvq_vq_set_refine (dvq_api.cu); 0 = default
 size_t vq_refine_binned_bytes(int64_t N);
 size_t vq_refine_binned_zero_bytes();
 int launch_vq_refine_binned(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,

@@ -261,6 +261,11 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
 
 }  // namespace
 
+// true when the per-row kernel can keep the whole FP32 codebook in shared memory (its fast regime)
+bool vq_refine_codebook_in_smem(int K, int D) {
+  return (size_t)K * (D + 4) * sizeof(float) + (size_t)(RTHREADS / 32) * 2 * D * sizeof(float) <= 200 * 1024;
+}
+
 bool vq_refine_supported(int K, int D) { return (D == 16 || D == 32 || D == 64 || D == 128 || D == 256 || D == 512) && K >= 32; }
 
 template <int DT>
@@ -269,7 +274,7 @@ static int launch_refine_dt(const float* z, const float* E, const float* ee, int
                             const int* n_list, int gshift, const int* ovf_last, const int* n_ovf, int sm_count, cudaStream_t s) {
   const size_t zbuf_bytes = (size_t)(RTHREADS / 32) * 2 * DT * sizeof(float);
   const size_t smem_e = (size_t)K * (DT + 4) * sizeof(float);
-  const bool in_smem = smem_e + zbuf_bytes <= 200 * 1024;
+  const bool in_smem = vq_refine_codebook_in_smem(K, DT);
 #define DVQ_LAUNCH_REFINE(TR_, SM_)                                                                                      \
   do {                                                                                                                   \
     const size_t bytes = zbuf_bytes + (SM_ ? smem_e : 0);                                                                \

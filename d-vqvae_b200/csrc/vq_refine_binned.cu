@@ -50,18 +50,19 @@ __device__ __forceinline__ int64_t listed_row(int i, int n, const int* __restric
   return i < n ? row_list[i] : ovf_last[-(int64_t)(i - n)];   // the overflow list is stored downwards from the end
 }
 
-// candidate sub-chunks of listed row i as (count, callback over sub-chunk indices)
+// candidate sub-chunks of a listed row, spread over a group of `gs` lanes (gl = lane inside the group)
 template <typename F>
-__device__ __forceinline__ void for_each_candidate(unsigned cand, bool all, bool list_mode, int nbins, int lane, F&& f) {
+__device__ __forceinline__ void for_each_candidate(unsigned cand, bool all, bool list_mode, int nbins, int gl, int gs, F&& f) {
   if (all) {
-    for (int b = lane; b < nbins; b += 32) f(b);
+    for (int b = gl; b < nbins; b += gs) f(b);
   } else if (list_mode) {
-    if (lane < 3) {
-      const int e = (int)((cand >> (10 * lane)) & 1023u) - 1;
+    for (int k = gl; k < 3; k += gs) {
+      const int e = (int)((cand >> (10 * k)) & 1023u) - 1;
       if (e >= 0 && e < nbins) f(e);
     }
   } else {
-    if (lane < 31 && ((cand >> lane) & 1u) && lane < nbins) f(lane);
+    for (int b = gl; b < 31 && b < nbins; b += gs)
+      if ((cand >> b) & 1u) f(b);
   }
 }
 __device__ __forceinline__ bool cand_is_all(unsigned cand, bool listed_normal, bool list_mode) {
@@ -81,23 +82,39 @@ refine_prep_kernel(const float* __restrict__ z, int D, int K, float* __restrict_
   const int nbins = (K + 31) / 32;
   for (int b = tid; b < nbins; b += PREP_THREADS) s_cnt[b] = 0;
   __syncthreads();
+  // Four rows per warp (8 lanes each) so that four independent row fetches are in flight per warp.  ||z||^2 is
+  // bit-identical to vq_simt_fp32.cu's (lane l of a 32-lane warp accumulates elements l, l + 32, ... with fmaf,
+  // then an xor-shuffle tree): lane j of a group plays the virtual lanes j, j + 8, j + 16, j + 24; the first two
+  // tree levels (xor 16, xor 8) are in-thread sums of the same operand pairs, the last three are shuffles.
   const int wtotal = gridDim.x * (PREP_THREADS / 32);
+  const int g = lane >> 3, j = lane & 7;
   int my_pairs = 0;
-  for (int i = blockIdx.x * (PREP_THREADS / 32) + warp; i < n + n2; i += wtotal) {
-    const int64_t row = listed_row(i, n, row_list, ovf_last);
-    const unsigned cand = i < n ? (unsigned)cand_list[i] : 0u;
+  for (int base = (blockIdx.x * (PREP_THREADS / 32) + warp) * 4; base < n + n2; base += wtotal * 4) {
+    const int i = base + g;
+    const bool active = i < n + n2;
+    const int64_t row = active ? listed_row(i, n, row_list, ovf_last) : 0;
+    const unsigned cand = (active && i < n) ? (unsigned)cand_list[i] : 0u;
     const float* zr = z + row * D;
-    float s2 = 0.f;   // ||z||^2 exactly as vq_simt_fp32.cu computes it
+    float pm[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < D; c += 32) {
-      if (c + lane < D) { const float v = __ldg(zr + c + lane); s2 = fmaf(v, v, s2); }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int d = c + j + 8 * m;
+        if (d < D) { const float v = __ldg(zr + d); pm[m] = fmaf(v, v, pm[m]); }
+      }
     }
-    const float zz = warp_sum(s2);
-    if (lane == 0) {
-      zq[row * D] = zz;              // the row's z_q is rewritten by the emit kernel
-      idx64[row] = ~0ull;
+    float zz = (pm[0] + pm[2]) + (pm[1] + pm[3]);
+    zz += __shfl_xor_sync(0xffffffffu, zz, 4);
+    zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+    zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+    if (active) {
+      if (j == 0) {
+        zq[row * D] = zz;              // the row's z_q is rewritten by the emit kernel
+        idx64[row] = ~0ull;
+      }
+      const bool all = cand_is_all(cand, i < n, list_mode != 0);
+      for_each_candidate(cand, all, list_mode != 0, nbins, j, 8, [&](int b) { atomicAdd(&s_cnt[b], 1); ++my_pairs; });
     }
-    const bool all = cand_is_all(cand, i < n, list_mode != 0);
-    for_each_candidate(cand, all, list_mode != 0, nbins, lane, [&](int b) { atomicAdd(&s_cnt[b], 1); ++my_pairs; });
   }
   __syncthreads();
   for (int b = tid; b < nbins; b += PREP_THREADS) {
@@ -165,14 +182,26 @@ refine_scatter_kernel(int K, const int* __restrict__ cand_list, int* __restrict_
   }
   for (int b = tid; b < nbins; b += PREP_THREADS) s_cnt[b] = 0;
   __syncthreads();
-  // this CTA's contiguous share of the listed rows: count, reserve, place
+  // this CTA's contiguous share of the listed rows: count, reserve, place.  One thread per row (a row has two or
+  // three candidates); rows paired with every sub-chunk are spread over the warp.
   const int per = (n + n2 + gridDim.x - 1) / gridDim.x;
   const int i0 = blockIdx.x * per, i1 = min(n + n2, i0 + per);
-  for (int i = i0 + warp; i < i1; i += PREP_THREADS / 32) {
-    const unsigned cand = i < n ? (unsigned)cand_list[i] : 0u;
-    const bool all = cand_is_all(cand, i < n, list_mode != 0);
-    for_each_candidate(cand, all, list_mode != 0, nbins, lane, [&](int b) { atomicAdd(&s_cnt[b], 1); });
-  }
+  auto sweep = [&](auto&& f) {
+    for (int ib = i0 + warp * 32; ib < i1; ib += PREP_THREADS) {
+      const int i = ib + lane;
+      const bool active = i < i1;
+      const unsigned cand = (active && i < n) ? (unsigned)cand_list[i] : 0u;
+      const bool all = active && cand_is_all(cand, i < n, list_mode != 0);
+      if (active && !all) for_each_candidate(cand, false, list_mode != 0, nbins, 0, 1, [&](int b) { f(b, i); });
+      unsigned am = __ballot_sync(0xffffffffu, all);
+      while (am) {
+        const int ii = ib + __ffs(am) - 1;
+        am &= am - 1u;
+        for (int b = lane; b < nbins; b += 32) f(b, ii);
+      }
+    }
+  };
+  sweep([&](int b, int) { atomicAdd(&s_cnt[b], 1); });
   __syncthreads();
   for (int b = tid; b < nbins; b += PREP_THREADS) {
     const int c = s_cnt[b];
@@ -180,11 +209,7 @@ refine_scatter_kernel(int K, const int* __restrict__ cand_list, int* __restrict_
     s_cnt[b] = 0;
   }
   __syncthreads();
-  for (int i = i0 + warp; i < i1; i += PREP_THREADS / 32) {
-    const unsigned cand = i < n ? (unsigned)cand_list[i] : 0u;
-    const bool all = cand_is_all(cand, i < n, list_mode != 0);
-    for_each_candidate(cand, all, list_mode != 0, nbins, lane, [&](int b) { pairs[s_base[b] + atomicAdd(&s_cnt[b], 1)] = i; });
-  }
+  sweep([&](int b, int i) { pairs[s_base[b] + atomicAdd(&s_cnt[b], 1)] = i; });
 }
 
 // order-preserving unsigned image of a float (NaN-free input)
@@ -199,7 +224,7 @@ refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, co
                     const float* __restrict__ zq, unsigned long long* __restrict__ idx64, const int* __restrict__ row_list,
                     const int* __restrict__ ovf_last, const int* __restrict__ pairs, const int* __restrict__ counters,
                     BinTables bt, long long pair_cap, int list_mode) {
-  extern __shared__ __align__(16) float smem_f[];   // zs[warps][RB][DS]
+  extern __shared__ __align__(16) float smem_f[];   // zs[warps][2][RB][DS]
   __shared__ int s_start[MAX_BINS + 1];
   __shared__ int s_items[MAX_BINS + 1];
   constexpr int NW = PAIR_THREADS / 32;
@@ -212,7 +237,7 @@ refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, co
   __syncthreads();
   const int ch = bt.item_start[MAX_BINS + 1];
   const int items = s_items[nbins];
-  float* zs = smem_f + warp * RB * DS;
+  float* zs = smem_f + warp * 2 * RB * DS;   // two halves: one being read, one being filled
   const int ns = D / DS;
   for (int item = blockIdx.x * NW + warp; item < items; item += gridDim.x * NW) {
     // bucket of this item: the last b with item_start[b] <= item
@@ -236,14 +261,37 @@ refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, co
         e[d] = v.x; e[d + 1] = v.y; e[d + 2] = v.z; e[d + 3] = v.w;
       }
     }
+    // Software pipeline over the (batch, slice) steps of the item: the z rows of the next step are copied into the
+    // other half of the warp's staging buffer with cp.async (zero-filled for missing rows), and the
+    // (row, ||z||^2) records of the next batch are read, while the current step is computed.
+    constexpr int ZL = RB * (DS / 4) / 32;   // 16-byte pieces per lane of one staged slice
+    auto fetch_rows = [&](int p, int64_t& row_, float& zz_) {
+      row_ = -1; zz_ = 0.f;
+      if (p < p1 && lane < min(RB, p1 - p)) {
+        row_ = listed_row(pairs[p + lane], n, row_list, ovf_last);
+        zz_ = zq[row_ * D];
+      }
+    };
+    auto stage_z = [&](int64_t row_, int sl, int buf) {
+#pragma unroll
+      for (int k = 0; k < ZL; ++k) {
+        const int f = k * 32 + lane;
+        const int r = f / (DS / 4), c4 = f - r * (DS / 4);
+        const long long rr = __shfl_sync(0xffffffffu, (long long)row_, r);
+        const float* src = rr >= 0 ? z + rr * D + sl * DS + c4 * 4 : z;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(zs + buf * RB * DS + r * DS + c4 * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(rr >= 0 ? 16 : 0) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int64_t row, row_n;
+    float zz, zz_n;
+    int buf = 0;
+    fetch_rows(p0, row, zz);
+    stage_z(row, 0, 0);
     for (int p = p0; p < p1; p += RB) {
       const int nb = min(RB, p1 - p);
-      int64_t row = -1;
-      float zz = 0.f;
-      if (lane < nb) {
-        row = listed_row(pairs[p + lane], n, row_list, ovf_last);
-        zz = zq[row * D];
-      }
+      fetch_rows(p + RB, row_n, zz_n);
       float acc[RB];
 #pragma unroll
       for (int r = 0; r < RB; ++r) acc[r] = 0.f;
@@ -255,22 +303,19 @@ refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, co
             e[d] = v.x; e[d + 1] = v.y; e[d + 2] = v.z; e[d + 3] = v.w;
           }
         }
+        __syncwarp();   // the previous step's reads of the other half are done
+        if (sl + 1 < ns) stage_z(row, sl + 1, buf ^ 1);
+        else if (p + RB < p1) stage_z(row_n, 0, buf ^ 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");   // keep one group per step
+        asm volatile("cp.async.wait_group 1;" ::: "memory");         // this step's rows have landed
         __syncwarp();
-        // stage this slice of the batch's z rows (coalesced DS*4-byte segments); missing rows read as zero
-#pragma unroll
-        for (int f = lane; f < RB * (DS / 4); f += 32) {
-          const int r = f / (DS / 4), c4 = f - r * (DS / 4);
-          const long long rr = __shfl_sync(0xffffffffu, (long long)row, r);
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rr >= 0) v = ldg4(z + rr * D + sl * DS + c4 * 4);
-          *reinterpret_cast<float4*>(zs + r * DS + c4 * 4) = v;
-        }
-        __syncwarp();
+        const float* zb = zs + buf * RB * DS;
+        buf ^= 1;
 #pragma unroll
         for (int d = 0; d < DS; d += 4) {
 #pragma unroll
           for (int r = 0; r < RB; ++r) {
-            const float4 z4 = *reinterpret_cast<const float4*>(zs + r * DS + d);   // broadcast read
+            const float4 z4 = *reinterpret_cast<const float4*>(zb + r * DS + d);   // broadcast read
             acc[r] = fmaf(z4.x, e[d], acc[r]);
             acc[r] = fmaf(z4.y, e[d + 1], acc[r]);
             acc[r] = fmaf(z4.z, e[d + 2], acc[r]);
@@ -291,6 +336,7 @@ refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, co
           if (lane == 0) atomicMin(idx64 + rr, ((unsigned long long)kmin << 32) | (unsigned)(b * 32 + src));
         }
       }
+      row = row_n; zz = zz_n;
     }
   }
 }
@@ -306,28 +352,33 @@ refine_emit_kernel(const float* __restrict__ z, const float* __restrict__ E, int
   const long long total = counters[C_PAIRS];
   if (n + n2 == 0 || total > pair_cap || total >= (1ll << 30)) return;
   const int wtotal = gridDim.x * (PREP_THREADS / 32);
+  const int g = lane >> 3, j = lane & 7;   // four rows per warp, 8 lanes each: four independent fetch chains in flight
   double lsse = 0.0;
-  for (int i = blockIdx.x * (PREP_THREADS / 32) + warp; i < n + n2; i += wtotal) {
-    const int64_t row = listed_row(i, n, row_list, ovf_last);
-    const unsigned long long best = idx64[row];
+  for (int base = (blockIdx.x * (PREP_THREADS / 32) + warp) * 4; base < n + n2; base += wtotal * 4) {
+    const int i = base + g;
+    const bool active = i < n + n2;
+    const int64_t row = active ? listed_row(i, n, row_list, ovf_last) : 0;
+    const unsigned long long best = active ? idx64[row] : 0ull;
     const int bidx = best == ~0ull ? 0 : (int)(best & 0xffffffffull);
     float* orow = zq + row * D;
     const float* erow = E + (int64_t)bidx * D;
     const float* zsrc = z + row * D;
-    for (int c = lane * 4; c < D; c += 128) {
-      const float4 e4 = ldg4(erow + c);
-      float4 o4 = e4;
-      if (TRAIN) {
-        const float4 z4 = ldg4(zsrc + c);
-        const float dx = __fsub_rn(e4.x, z4.x), dy = __fsub_rn(e4.y, z4.y);
-        const float dz = __fsub_rn(e4.z, z4.z), dw = __fsub_rn(e4.w, z4.w);
-        lsse += (double)dx * dx + (double)dy * dy + (double)dz * dz + (double)dw * dw;
-        o4 = make_float4(__fadd_rn(z4.x, dx), __fadd_rn(z4.y, dy), __fadd_rn(z4.z, dz), __fadd_rn(z4.w, dw));
+    if (active) {
+      for (int c = j * 4; c < D; c += 32) {
+        const float4 e4 = ldg4(erow + c);
+        float4 o4 = e4;
+        if (TRAIN) {
+          const float4 z4 = ldg4(zsrc + c);
+          const float dx = __fsub_rn(e4.x, z4.x), dy = __fsub_rn(e4.y, z4.y);
+          const float dz = __fsub_rn(e4.z, z4.z), dw = __fsub_rn(e4.w, z4.w);
+          lsse += (double)dx * dx + (double)dy * dy + (double)dz * dz + (double)dw * dw;
+          o4 = make_float4(__fadd_rn(z4.x, dx), __fadd_rn(z4.y, dy), __fadd_rn(z4.z, dz), __fadd_rn(z4.w, dw));
+        }
+        *reinterpret_cast<float4*>(orow + c) = o4;
       }
-      *reinterpret_cast<float4*>(orow + c) = o4;
     }
-    __syncwarp();   // every lane has read idx64[row] before it is overwritten
-    if (lane == 0) {
+    __syncwarp();   // every lane of the group has read idx64[row] before it is overwritten
+    if (active && j == 0) {
       idx64[row] = (unsigned long long)bidx;
       if (TRAIN) atomicAdd(hist + bidx, 1ull);
     }
@@ -358,7 +409,8 @@ int launch_vq_refine_binned(const float* z, const float* E, const float* ee, int
   BinTables bt;
   bt.count = wi; bt.cursor = wi + MAX_BINS; bt.start = wi + 2 * MAX_BINS; bt.item_start = wi + 3 * MAX_BINS + 1;
   int* pairs = reinterpret_cast<int*>(static_cast<char*>(ws) + align_up(sizeof(int) * (size_t)(4 * MAX_BINS + 8), 256));
-  const long long pair_cap = 2 * (long long)N;
+  const long long cap_override = refine_pair_cap_override();
+  const long long pair_cap = (cap_override > 0 && cap_override < 2 * (long long)N) ? cap_override : 2 * (long long)N;
   const int* ovf_last = row_list + (N - 1);
   unsigned long long* idx64 = reinterpret_cast<unsigned long long*>(idx);
   const int pair_grid = dp.sm_count;
@@ -369,7 +421,7 @@ int launch_vq_refine_binned(const float* z, const float* E, const float* ee, int
   DVQ_CUDA_CHECK(cudaGetLastError());
   refine_scatter_kernel<<<dp.sm_count, PREP_THREADS, 0, s>>>(K, cand_list, counters, bt, pairs, pair_cap, list_mode, pair_warps);
   DVQ_CUDA_CHECK(cudaGetLastError());
-  const size_t smem = (size_t)(PAIR_THREADS / 32) * RB * DS * sizeof(float);
+  const size_t smem = (size_t)(PAIR_THREADS / 32) * 2 * RB * DS * sizeof(float);
 #define DVQ_LAUNCH_PAIRS(DS_)                                                                                              \
   do {                                                                                                                     \
     DVQ_CUDA_CHECK(cudaFuncSetAttribute(refine_pairs_kernel<DS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -46,14 +46,22 @@ namespace {
 
 constexpr int TM = 128;                 // rows per tile
 constexpr int A_CHUNK_BYTES = TM * 16 + 32;  // one 8-wide k-chunk of the A image (+32 B: bank spreading)
-constexpr int CONV_WARP0 = 2;
-constexpr int EPI_WARP0 = 6;
+// Warp roles are laid out in aligned groups of four (warpgroups) so that a group can resize its register
+// allocation with setmaxnreg: warps 0-3 producer / MMA issuer / codebook streamer / spare, 4-7 converters,
+// 8-19 epilogue (three warpgroups: one warp per TMEM lane quarter each), 20-23 gather.
+constexpr int BLOAD_WARP = 2;                // codebook streamer (active when the image is not resident)
+constexpr int CONV_WARP0 = 4;
+constexpr int EPI_WARP0 = 8;
 constexpr int EPQ = 3;                       // epilogue warps per TMEM lane quarter (they split the columns)
 constexpr int EPI_WARPS = 4 * EPQ;
 constexpr int GATHER_WARP0 = EPI_WARP0 + EPI_WARPS;
 constexpr int GATHER_WARPS = 4;
-constexpr int BLOAD_WARP = GATHER_WARP0 + GATHER_WARPS;   // codebook streamer (active when the image is not resident)
-constexpr int NUM_WARPS = BLOAD_WARP + 1;
+constexpr int NUM_WARPS = GATHER_WARP0 + GATHER_WARPS;
+// The launch gives each of the 768 threads 80 registers (warp allocations come in units of 512).  The control
+// group hands 32 per thread back and the gather group takes them: its two batches of 128-bit loads in flight
+// (plus the z rows requested ahead of the codes) do not fit 80.  The trade must balance inside the CTA's own
+// allocation — setmaxnreg.inc only draws from what the CTA released: 128 * (48 + 80 + 112) + 384 * 80 = 61 440.
+constexpr int REGS_CTRL = 48, REGS_GATHER = 112;
 constexpr int DSLICE = 64;                   // e_dim is contracted in slices of at most 64 columns
 // slice width: the whole row up to 64 columns, 64-column slices up to e_dim 256, 32-column slices for e_dim 512
 // (the resident A image of 128 x 528 halfs leaves room for only small staging / ring slots)
@@ -498,6 +506,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   tc::tc_fence_after();
   const uint32_t tmem_base = ctl.tmem_slot;
 
+  if (warp < CONV_WARP0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));   // whole warpgroup, before the roles split
   if (warp == 0) {
     // ===================== producer: z tile (slices) -> staging ring =====================
     {
@@ -645,6 +655,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 #endif
       STAT_FLUSH(3, 1);
     }
+  }   // (warp 3 is the spare of the control warpgroup: nothing to do until the final barrier)
   } else if (warp < EPI_WARP0) {
     // ===================== converters: thread <-> tile row =====================
     const int r = (warp - CONV_WARP0) * 32 + lane;
@@ -891,6 +902,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     STAT_FLUSH(5, 7);
   } else {
     // ===================== gather: z_q, idx, SSE, histogram for the decided rows =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_GATHER));
     const int gw = warp - GATHER_WARP0;
     int* shist = reinterpret_cast<int*>(smem + L.hist);
     const int nv = D / 4;                              // float4 slots per row (power of two)
@@ -906,7 +918,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     const int nsteps = rows_per_warp / rps;            // row-steps per warp per tile (per part)
     const int rbase = gw * rows_per_warp + rsub;
     double sse_acc = 0.0;
-    constexpr int U = 8;                               // row-steps in flight per lane (x2 loads in train mode)
+    constexpr bool PREFETCH_Z = true;                  // request the first batch's z rows before the codes arrive (needs ~16 more registers)
+    constexpr int UH = 4;                              // row-steps per batch; two batches in flight per lane (x2 loads in train mode)
     STAT_DECL(2);
 #ifdef DVQ_TC_STATS
     const long long g_t0 = clock64();
@@ -916,6 +929,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int64_t row0 = tile * TM;
       const int rows = (int)min((int64_t)TM, p.N - row0);
       const int slot = (int)(it & 1);
+      // Two batches of UH row-steps are kept in flight (software pipeline: the loads of batch b + 1 are issued
+      // before batch b is consumed), and the z rows of the first batch — they do not depend on the codes — are
+      // requested before this tile's codes arrive, so that only one L2 round trip per tile is exposed.
+      float4 eA[UH], zA[UH], eB[UH], zB[UH];
+      int kA[UH], kB[UH];
+      const bool full_tile = rows == TM;
+      const bool piped = full_tile && (nsteps % (2 * UH)) == 0;
+      const float* zp0 = p.z + (row0 + rbase) * D + c4_lane * 4;
+      if (TRAIN && piped && PREFETCH_Z) {
+#pragma unroll
+        for (int u = 0; u < UH; ++u) zA[u] = __ldcs(reinterpret_cast<const float4*>(zp0 + (int64_t)(u * rps) * D));
+      }
       { STAT_T0(); nb_sync(NB_SIDX_FULL + slot, NB_SIDX_THREADS); STAT_ADD(0); }
       if (gw == 0) TRACE(4, 0, 0);
       const int* sp = reinterpret_cast<const int*>(smem + L.sidx) + slot * TM + rbase;
@@ -949,28 +974,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         }
       }
       float lsse = 0.f;
-      const bool full_tile = rows == TM;
 #pragma unroll 1
       for (int part = 0; part < parts; ++part) {
         const int c4 = (part << 5) | c4_lane;
         const char* ec = reinterpret_cast<const char*>(p.E + c4 * 4);
         const float* zp = p.z + (row0 + rbase) * D + c4 * 4;
         float* op = p.zq + (row0 + rbase) * D + c4 * 4;
-        if (full_tile && (nsteps % U) == 0) {
-          // fast path: no per-row checks, loads of a whole batch issued before any is consumed
-#pragma unroll 1
-          for (int t0 = 0; t0 < nsteps; t0 += U) {
-            float4 e4[U], z4[U];
-            int kk[U];
+        if (piped) {
+          // fast path: no per-row checks
+          auto issue = [&](int t0, float4 (&e4)[UH], float4 (&z4)[UH], int (&kk)[UH], bool have_z) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) kk[u] = sp[(t0 + u) * rps];
+            for (int u = 0; u < UH; ++u) kk[u] = sp[(t0 + u) * rps];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
+            for (int u = 0; u < UH; ++u) {
               e4[u] = __ldg(reinterpret_cast<const float4*>(ec + (uint32_t)max(kk[u], 0)));   // undecided: any valid row
-              if (TRAIN) z4[u] = __ldcs(reinterpret_cast<const float4*>(zp + (int64_t)((t0 + u) * rps) * D));   // last use of this tile
+              if (TRAIN && !have_z) z4[u] = __ldcs(reinterpret_cast<const float4*>(zp + (int64_t)((t0 + u) * rps) * D));   // last use of this tile
             }
+          };
+          auto finish = [&](int t0, const float4 (&e4)[UH], const float4 (&z4)[UH], const int (&kk)[UH]) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
+            for (int u = 0; u < UH; ++u) {
               float4 o4 = e4[u];
               if (TRAIN) {
                 // packed FP32 (FADD2 / FMUL2 / FFMA2): d = fl(e - z), z_q = fl(z + d), two elements per instruction,
@@ -987,6 +1010,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
               }
               __stcs(reinterpret_cast<float4*>(op + (int64_t)((t0 + u) * rps) * D), o4);   // streaming: never re-read
             }
+          };
+          issue(0, eA, zA, kA, PREFETCH_Z && part == 0);   // part 0: the z rows of the first batch were requested before the barrier
+#pragma unroll 1
+          for (int t0 = 0; t0 < nsteps; t0 += 2 * UH) {
+            issue(t0 + UH, eB, zB, kB, false);
+            finish(t0, eA, zA, kA);
+            if (t0 + 2 * UH < nsteps) issue(t0 + 2 * UH, eA, zA, kA, false);
+            finish(t0 + UH, eB, zB, kB);
           }
         } else {
 #pragma unroll 1

@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdvq_sm100.so")
+# DVQ_LIB selects an instrumented build of the same library (DVQ_TC_STATS=1 python d-vqvae_b200/build.py); default: the in-tree release build
+LIB_PATH = os.environ.get("DVQ_LIB") or os.path.join(_HERE, "libdvq_sm100.so")
 
 ABI_VERSION = 1
 DVQ_TRAIN = 0x1
@@ -30,6 +31,7 @@ SYMBOLS = {
     "dvq_last_error": (C.c_char_p, []),
     "dvq_launch_count": (C.c_longlong, []),
     "dvq_profile_enable": (_i, [_i]),
+    "dvq_vq_set_refine": (_i, [_i, C.c_longlong]),
     "dvq_profile_mean": (_i, [C.POINTER(_f), C.POINTER(_i), _i]),
     "dvq_debug_umma": (_i, [_vp, C.c_uint32, _vp, C.c_uint32, _i, C.POINTER(C.c_uint32), C.c_uint32, _i, _vp, _vp, _vp]),
     "dvq_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),

@@ -67,6 +67,13 @@ DVQ_API long long dvq_launch_count(void);
 DVQ_API int dvq_profile_enable(int on);
 DVQ_API int dvq_profile_mean(float* ms, int* count, int n);
 
+/* Test / measurement hook for the exact refine stage of the tcgen05 path (both variants give identical
+ * results): mode 0 = automatic (per-row kernel while the FP32 codebook fits its shared memory, binned
+ * kernels otherwise), 1 = per-row kernel only, 2 = binned kernels; pair_cap > 0 overrides the capacity
+ * of the binned (row, sub-chunk) pair list (default 2 N) so that tests can exercise the device-side
+ * hand-back to the per-row kernel, <= 0 restores the default.  Process-wide. */
+DVQ_API int dvq_vq_set_refine(int mode, long long pair_cap);
+
 /* Diagnostic used by tests/test_tc_probe_gpu.py: run `ksteps` tcgen05.mma (M=128, N=n_cols,
  * kind::f16) on caller-built shared-memory operand images and dump the [128,n_cols] fp32
  * accumulator.  strides = {a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep} in bytes; *err (device
