@@ -37,6 +37,7 @@ sys.path.insert(0, os.path.join(ROOT, "d-vqvae_b200"))
 N_PER_GPU = 4194304
 E_DIM = 64
 N_E = 512
+E2E_CHUNK_ROWS = 262144          # rows per chunk of the host-buffer pipeline (e2e leg)
 AL, BETA = 1.0, 0.25
 METRIC = "vq_latents_per_sec"
 UNIT = "latents/s"
@@ -179,6 +180,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 10))")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunk-rows", type=int, default=E2E_CHUNK_ROWS, help="rows per chunk of the host-buffer pipeline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -255,7 +257,7 @@ def main():
 
     # ---- e2e: host buffers through dvq_vq_forward_host --------------------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 10)
-    hq = dvq.HostQuantizer(chunk_rows=262144, n_e_max=N_E, e_dim_max=E_DIM, device=dev)
+    hq = dvq.HostQuantizer(chunk_rows=args.e2e_chunk_rows, n_e_max=N_E, e_dim_max=E_DIM, device=dev)
     z_host = torch.empty((N_PER_GPU, E_DIM), dtype=torch.float32, pin_memory=True)
     z_host.copy_(z)
     E_host = vq.embedding.weight.detach().cpu().pin_memory()
@@ -308,7 +310,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_PER_GPU * E_DIM * 4 + N_E * E_DIM * 4,
                     "d2h_bytes_per_step": N_PER_GPU * E_DIM * 4 + N_PER_GPU * 8 + 8, "steps": e2e_steps,
-                    "ms_per_step": e2e_s / e2e_steps * 1e3, "api": "dvq_vq_forward_host (pinned host buffers, 3-stream chunk pipeline)",
+                    "ms_per_step": e2e_s / e2e_steps * 1e3, "api": "dvq_vq_forward_host (pinned host buffers, 3-stream chunk pipeline, %d-row chunks)" % args.e2e_chunk_rows,
                     "indices_equal_device_path": same_idx},
             "gpu_launches": launches, "clocks": clocks,
         }

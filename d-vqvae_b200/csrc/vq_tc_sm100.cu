@@ -21,16 +21,18 @@
 // 2*eps_n of the minimum; the count of such keys is kept with a running (never too small) threshold,
 // exact resets, and FFMA.SAT / FFMA2 arithmetic on the FMA pipe.  Undecided rows (a few %) go to the list.
 //
-// Pipeline (one persistent CTA per SM, 22 warps; every SM sub-partition hosts 1 converter, 3 epilogue
-// and 1 gather warp):
-//   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B),
-//                          codebook chunks -> 2-slot ring when K > 512
+// Pipeline (one persistent CTA per SM, 24 warps in six warpgroups; every SM sub-partition hosts 1 converter,
+// 3 epilogue and 1 gather warp):
+//   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B)
 //   warp 1      MMA      : one elected lane issues tcgen05.mma from uniform-register descriptors; the warp
 //                          then waits for the chunk's commit mbarrier and relays it on named barriers
-//   warps 2-5   convert  : staging -> scales / norms / bounds -> FP16 A image (2 stages)
-//   warps 6-17  epilogue : tcgen05.ld TMEM -> min tree + ambiguity masks per 32-code sub-chunk; three warps
+//   warp 2      streamer : codebook chunks -> 2-slot ring when the operand image is not resident (warp 3: spare)
+//   warps 4-7   convert  : staging -> scales / norms / bounds -> FP16 A image (2 stages)
+//   warps 8-19  epilogue : tcgen05.ld TMEM -> min tree + ambiguity masks per 32-code sub-chunk; three warps
 //                          per TMEM lane quarter split the columns, the owner merges and writes idx / histogram
-//   warps 18-21 gather   : E[idx] (128-bit, 8-16 loads in flight per lane), z_q, SSE, refine-list append
+//   warps 20-23 gather   : E[idx] (128-bit loads, two batches in flight per lane, z rows requested before the
+//                          codes arrive), z_q, SSE, refine-list append
+// The control warpgroup (warps 0-3) releases registers with setmaxnreg and the gather warpgroup takes them.
 // Warp-to-warp hand-offs are hardware named barriers (bar.arrive / bar.sync), mbarriers only where the
 // async proxy signals.  TMEM: 512 columns = 2 accumulator stages of 256, so the MMA of one 256-code
 // chunk overlaps the epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays
