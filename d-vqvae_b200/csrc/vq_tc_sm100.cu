@@ -39,6 +39,7 @@
 // resident in shared memory for K <= 512 and is streamed per row tile above.
 #include <cuda_fp16.h>
 #include <cstddef>
+#include <cstdlib>
 
 #include "dvq_common.cuh"
 #include "tc_prims.cuh"
@@ -138,7 +139,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
     L.stage[0] = off; off += L.stage_bytes;
     L.stage[1] = off; off += L.stage_bytes;
     L.meta = off; off += META_SLOTS * TM * 4;
-    L.fin = off; off += (EPQ - 1) * TM * 16;   // (EPQ-1) helper warps x (key, col, cnt, cand); single slot
+    L.fin = off; off += EPQ * TM * 16;         // up to EPQ helper warps (EPQ + 1 warps per quarter when the converters join) x (key, col, cnt, cand); single slot
     L.sidx = off; off += 2 * TM * 4;      // 2 slots of the hand-off word (code offset | undecided flag + candidates)
     L.hist = off; off += L.hist_in_smem ? (uint32_t)K * 4 : 0u;
     L.total = off;
@@ -342,11 +343,12 @@ enum BarId { B_STAGE_FULL = 0, B_STAGE_EMPTY = 2, B_ACC_FULL = 4, B_B_FULL = 6, 
 // tile when the helpers are ready for the next one.
 enum NamedBarId { NB_ACC_FULL_OWN = 1, NB_ACC_FULL_HLP = 3, NB_ACC_EMPTY = 5, NB_A_FULL = 7, NB_FIN_FULL = 9, NB_FIN_EMPTY = 10,
                   NB_SIDX_FULL = 11, NB_SIDX_EMPTY = 13 };
-constexpr int NB_ACC_THREADS = 32 + EPI_WARPS * 32;          // MMA warp + epilogue warps
-constexpr int NB_ACC_OWN_THREADS = 32 + 4 * 32;              // MMA warp + owner warps
-constexpr int NB_ACC_HLP_THREADS = 32 + (EPI_WARPS - 4) * 32;   // MMA warp + helper warps
+// (epq = warps per TMEM lane quarter that run the filter: EPQ, or EPQ + 1 when the converter warps join in)
+__host__ __device__ constexpr int nb_acc_threads(int epq) { return 32 + 4 * epq * 32; }            // MMA warp + filter warps
+constexpr int NB_ACC_OWN_THREADS = 32 + 4 * 32;                                                     // MMA warp + owner warps
+__host__ __device__ constexpr int nb_acc_hlp_threads(int epq) { return 32 + 4 * (epq - 1) * 32; }  // MMA warp + helper warps
+__host__ __device__ constexpr int nb_fin_threads(int epq) { return 4 * epq * 32; }                  // owners + helpers
 constexpr int NB_A_THREADS = 32 + 128;                       // MMA warp + converter warps
-constexpr int NB_FIN_THREADS = EPI_WARPS * 32;               // owners + helpers
 constexpr int NB_SIDX_THREADS = 4 * 32 + GATHER_WARPS * 32;  // owner epilogue warps + gather warps
 struct Ctl {
   uint64_t bars[NBARS];
@@ -464,8 +466,13 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
 // DT > 0: e_dim known at compile time (strides, trip counts and index masks become immediates and the
 // role loops unroll); DT == 0: generic.  TRAIN selects the straight-through / SSE / histogram epilogue.
 // LIST selects the candidate record of the undecided rows (see cand_union): sub-chunk list for large codebooks.
-template <int DT, bool TRAIN, bool LIST>
+// CE: the converter warps join the filter as a fourth warp per TMEM lane quarter (streamed codebooks with a
+// double-buffered A image: a tile then has many accumulator chunks and the converters would idle for most of it;
+// with four warps per quarter every warp takes exactly two of a chunk's eight sub-chunks instead of 3 / 3 / 2).
+template <int DT, bool TRAIN, bool LIST, bool CE>
 __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
+  constexpr int EPQX = CE ? EPQ + 1 : EPQ;       // filter warps per TMEM lane quarter
+  constexpr int NB_ACC_THREADS = nb_acc_threads(EPQX), NB_ACC_HLP_THREADS = nb_acc_hlp_threads(EPQX), NB_FIN_THREADS = nb_fin_threads(EPQX);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) Ctl ctl;   // every mbarrier + the error word: addressed as base + constant
   // the opaque move keeps the window addresses in registers (the compiler otherwise rematerialises the
@@ -507,6 +514,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = ctl.tmem_slot;
+
+  // ---- the filter over one row tile, shared by the epilogue warps and (CE) the converter warps -----------------
+  // wq: 0 = owner of the warp's rows, 1..EPQX-1 = helpers (they split the columns); r = tile row = TMEM lane.
+  // My sub-chunks of a 256-column chunk: every EPQX-th one; the owner takes the residue class with the fewest
+  // members when they are uneven (it also merges, writes idx and the histogram).  The sub-chunk loop is kept
+  // rolled so that the filter stays inside the instruction cache; the TMEM-load latency is covered by the other
+  // warps of the sub-partition.  Mask mode: one candidate bit per 32-code sub-chunk (K <= 992, see
+  // vq_tc_cand_gshift); list mode: sub-chunk index + 1.
+  auto filter_tile = [&](int64_t it, uint32_t& q, int wq, int r, RowState& st, float& band) {
+    const uint32_t lane_addr = (uint32_t)(r & ~31) << 16;
+    st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0; st.bits = 0u; st.col0 = 0; st.cand = 0u;
+    float band_big = 0.f;
+    const int sc0 = (wq + EPQX - 1) % EPQX;
+    for (int c = 0; c < nchunks; ++c, ++q) {
+      const uint32_t t = q & 1u;
+      if (wq == 0) nb_sync(NB_ACC_FULL_OWN + (int)t, NB_ACC_OWN_THREADS);
+      else nb_sync(NB_ACC_FULL_HLP + (int)t, NB_ACC_HLP_THREADS);
+      tc::tc_fence_after();
+      if (wq == 0 && r < 32) TRACE(1, 0, c & 1);
+      if (wq == 1 && r < 32) TRACE(2, 0, c & 1);
+      if (c == 0) {
+        band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
+        band_big = band * 1048576.f;
+      }
+      const int n = min(256, K - c * 256);
+      int col = c * 256 + sc0 * 32;
+      const int col_end = c * 256 + n;
+      uint32_t taddr = tmem_base + lane_addr + t * 256u + (uint32_t)sc0 * 32u;
+      uint32_t gbit = LIST ? (uint32_t)(c * 8 + sc0 + 1) : 1u << (c * 8 + sc0);
+#pragma unroll 1
+      for (; col < col_end; col += 32 * EPQX, taddr += 32u * EPQX, gbit = LIST ? gbit + EPQX : gbit << EPQX) {
+        uint32_t v[32];
+        tc::tmem_ld32(taddr, v);
+        tmem_ld_wait_dep(v);
+        filter_subchunk<LIST>(v, col, gbit, band, band_big, st);
+      }
+      tc::tc_fence_before();
+      if (wq == 0 && r < 32) TRACE(1, 1, c & 1);
+      if (wq == 1 && r < 32) TRACE(2, 1, c & 1);
+      if ((int64_t)q + 2 < total_chunks) nb_arrive(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS);
+    }
+  };
+  // a helper hands its partial result of the tile to the owner warp of the same rows (single slot per helper)
+  auto helper_handoff = [&](int64_t it, int wq, int r, const RowState& st) {
+    float* fin_key = reinterpret_cast<float*>(smem + L.fin) + (wq - 1) * 4 * TM;
+    if (it >= 1) nb_sync(NB_FIN_EMPTY, NB_FIN_THREADS);
+    fin_key[r] = st.m1;
+    reinterpret_cast<int*>(fin_key + TM)[r] = row_state_col(st);
+    reinterpret_cast<int*>(fin_key + 2 * TM)[r] = st.cnt;
+    reinterpret_cast<uint32_t*>(fin_key + 3 * TM)[r] = st.cand;
+    nb_arrive(NB_FIN_FULL, NB_FIN_THREADS);
+    if (wq == 1 && r < 32) TRACE(2, 2, 0);
+  };
 
   if (warp < CONV_WARP0) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));   // whole warpgroup, before the roles split
@@ -668,7 +728,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 #endif
     const int nvs = ds / 4;   // float4 per row of one slice
     uint32_t js = 0;          // running slice counter of the staging ring
-    for (int64_t it = 0; it < my_tiles; ++it) {
+    auto convert_tile = [&](int64_t it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int a = L.a_bufs == 2 ? (int)(it & 1) : 0;
       const uint32_t aph = L.a_bufs == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);   // phase of B_A_EMPTY[a] this tile waits past
@@ -773,6 +833,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       tc::fence_proxy_async_smem();           // A image visible to the tensor core (async proxy)
       nb_arrive(NB_A_FULL + (int)(it & 1), NB_A_THREADS);
       if (warp == CONV_WARP0) TRACE(3, 3, 0);
+    };
+    if (!CE) {
+      for (int64_t it = 0; it < my_tiles; ++it) convert_tile(it);
+    } else {
+      // The converters stay one tile ahead of the MMAs (double-buffered A image) and spend the rest of a tile as
+      // the fourth filter warp of their TMEM lane quarter: convert tile it + 1, then filter tile it as helper
+      // EPQX - 1.  While they convert, the accumulator chunks they have not read yet stay occupied — a few
+      // thousand cycles per tile against the tens of chunks a streamed codebook has.
+      uint32_t q = 0;
+      if (my_tiles > 0) convert_tile(0);
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        if (it + 1 < my_tiles) convert_tile(it + 1);
+        RowState st;
+        float band = 0.f;
+        filter_tile(it, q, EPQX - 1, r, st, band);
+        helper_handoff(it, EPQX - 1, r, st);
+      }
     }
 #ifdef DVQ_TC_STATS
     stat_acc[2] = clock64() - conv_t0;
@@ -785,7 +862,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     const int quarter = warp & 3;       // TMEM lanes this warp may access: 32*(warp_id % 4)
     const int wq = w >> 2;              // 0 = owner of these rows, 1..EPQ-1 = helpers (they split the columns)
     const int r = quarter * 32 + lane;  // tile row == TMEM lane
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     uint32_t q = 0;
     STAT_DECL(5);
 #ifdef DVQ_TC_STATS
@@ -797,58 +873,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int rows = (int)min((int64_t)TM, p.N - row0);
       const int slot = (int)(it & 1);
       RowState st;
-      st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0; st.bits = 0u; st.col0 = 0; st.cand = 0u;
-      float band = 0.f, band_big = 0.f;
-      for (int c = 0; c < nchunks; ++c, ++q) {
-        const uint32_t t = q & 1u;
-        {
-          STAT_T0();
-          if (wq == 0) nb_sync(NB_ACC_FULL_OWN + (int)t, NB_ACC_OWN_THREADS);
-          else nb_sync(NB_ACC_FULL_HLP + (int)t, NB_ACC_HLP_THREADS);
-          STAT_ADD(0);
-        }
-        tc::tc_fence_after();
-        if (w == 0) TRACE(1, 0, c & 1);
-        if (w == 4) TRACE(2, 0, c & 1);
-        if (c == 0) {
-          band = reinterpret_cast<const float*>(smem + L.meta)[(it & (META_SLOTS - 1)) * TM + r];
-          band_big = band * 1048576.f;
-        }
-        const int n = min(256, K - c * 256);
-        const uint32_t tbase = tmem_base + lane_addr + t * 256u;
-        // my sub-chunks of this chunk: every EPQ-th one; the owner warp (wq == 0) takes the residue class
-        // with the fewest members (it also merges, writes idx and the histogram).  The loop is kept rolled so the epilogue
-        // stays inside the instruction cache; the TMEM load latency is covered by the other warps of
-        // the sub-partition.
-        // (mask mode: one candidate bit per 32-code sub-chunk — K <= 992, see vq_tc_cand_gshift; list mode: sub-chunk index + 1)
-        const int sc0 = (wq + EPQ - 1) % EPQ;
-        int col = c * 256 + sc0 * 32;
-        const int col_end = c * 256 + n;
-        uint32_t taddr = tbase + (uint32_t)sc0 * 32u;
-        uint32_t gbit = LIST ? (uint32_t)(c * 8 + sc0 + 1) : 1u << (c * 8 + sc0);
-#pragma unroll 1
-        for (; col < col_end; col += 32 * EPQ, taddr += 32u * EPQ, gbit = LIST ? gbit + EPQ : gbit << EPQ) {
-          uint32_t v[32];
-          tc::tmem_ld32(taddr, v);
-          tmem_ld_wait_dep(v);
-          filter_subchunk<LIST>(v, col, gbit, band, band_big, st);
-        }
-        tc::tc_fence_before();
-        if (w == 0) TRACE(1, 1, c & 1);
-        if (w == 4) TRACE(2, 1, c & 1);
-        if ((int64_t)q + 2 < total_chunks) nb_arrive(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS);
-      }
+      float band = 0.f;
+      filter_tile(it, q, wq, r, st, band);
       float* fin_base = reinterpret_cast<float*>(smem + L.fin);   // single slot: phase flips every tile
       if (wq > 0) {
-        // hand this warp's partial result to the owner warp of the same rows
-        float* fin_key = fin_base + (wq - 1) * 4 * TM;
-        if (it >= 1) { STAT_T0(); nb_sync(NB_FIN_EMPTY, NB_FIN_THREADS); STAT_ADD(1); }
-        fin_key[r] = st.m1;
-        reinterpret_cast<int*>(fin_key + TM)[r] = row_state_col(st);
-        reinterpret_cast<int*>(fin_key + 2 * TM)[r] = st.cnt;
-        reinterpret_cast<uint32_t*>(fin_key + 3 * TM)[r] = st.cand;
-        nb_arrive(NB_FIN_FULL, NB_FIN_THREADS);
-        if (w == 4) TRACE(2, 2, 0);
+        helper_handoff(it, wq, r, st);
       } else {
         { STAT_T0(); nb_sync(NB_FIN_FULL, NB_FIN_THREADS); STAT_ADD(2); }
         if (w == 0) TRACE(1, 2, 0);
@@ -860,7 +889,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         uint32_t cand = st.cand;
         bool flag = false;
 #pragma unroll
-        for (int h = 0; h < EPQ - 1; ++h) {
+        for (int h = 0; h < EPQX - 1; ++h) {
           const float* fin_key = fin_base + h * 4 * TM;
           const float ko = fin_key[r];
           const int co = reinterpret_cast<const int*>(fin_key + TM)[r];
@@ -1121,18 +1150,29 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   p.ntiles = (N + TM - 1) / TM;
   const size_t smem = L.total + 128;
   const int64_t grid = p.ntiles < dp.sm_count ? p.ntiles : dp.sm_count;
-#define DVQ_LAUNCH_TC(DT_, TR_, LS_)                                                                                         \
+  // Converters join the filter as a fourth warp per TMEM lane quarter where that was measured to pay: single-slice
+  // shapes (e_dim <= 64) with at least 16 accumulator chunks per tile (+4 % at K >= 4096; with few chunks the
+  // serialisation against the conversion costs more than the extra warp gives, and the sliced shapes are bound by
+  // streaming the operand blocks, not by the filter).  Needs a streamed codebook and a double-buffered A image.
+  // DVQ_TC_CE=0 / 1 forces it off / on where possible (A/B runs).
+  static const char* ce_env = getenv("DVQ_TC_CE");
+  const bool streamed = ((K + 255) / 256) * (int)L.ns > 2;
+  const bool ce_ok = streamed && L.a_bufs == 2;
+  const bool ce = ce_ok && (ce_env ? ce_env[0] == '1' : (L.ns == 1 && (K + 255) / 256 >= 16));
+#define DVQ_LAUNCH_TC(DT_, TR_, LS_, CE_)                                                                                   \
   do {                                                                                                                 \
-    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<DT_, TR_, LS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    vq_tc_kernel<DT_, TR_, LS_><<<(unsigned)grid, NTHREADS, smem, s>>>(p);                                                  \
+    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<DT_, TR_, LS_, CE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    vq_tc_kernel<DT_, TR_, LS_, CE_><<<(unsigned)grid, NTHREADS, smem, s>>>(p);                                             \
   } while (0)
   const bool list = p.cand_gshift < 0;
-  if (D == 64 && !list) {
-    if (train) DVQ_LAUNCH_TC(64, true, false); else DVQ_LAUNCH_TC(64, false, false);
+  if (D == 64 && !list && !streamed) {
+    if (train) DVQ_LAUNCH_TC(64, true, false, false); else DVQ_LAUNCH_TC(64, false, false, false);
   } else if (!list) {
-    if (train) DVQ_LAUNCH_TC(0, true, false); else DVQ_LAUNCH_TC(0, false, false);
+    if (ce) { if (train) DVQ_LAUNCH_TC(0, true, false, true); else DVQ_LAUNCH_TC(0, false, false, true); }
+    else { if (train) DVQ_LAUNCH_TC(0, true, false, false); else DVQ_LAUNCH_TC(0, false, false, false); }
   } else {
-    if (train) DVQ_LAUNCH_TC(0, true, true); else DVQ_LAUNCH_TC(0, false, true);
+    if (ce) { if (train) DVQ_LAUNCH_TC(0, true, true, true); else DVQ_LAUNCH_TC(0, false, true, true); }
+    else { if (train) DVQ_LAUNCH_TC(0, true, true, false); else DVQ_LAUNCH_TC(0, false, true, false); }
   }
 #undef DVQ_LAUNCH_TC
   DVQ_CUDA_CHECK(cudaGetLastError());
