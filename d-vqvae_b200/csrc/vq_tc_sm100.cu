@@ -26,7 +26,8 @@
 //   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B)
 //   warp 1      MMA      : one elected lane issues tcgen05.mma from uniform-register descriptors; the warp
 //                          then waits for the chunk's commit mbarrier and relays it on named barriers
-//   warp 2      streamer : codebook chunks -> 2-slot ring when the operand image is not resident (warp 3: spare)
+//   warp 2      streamer : codebook chunks -> 2-slot ring when the operand image is not resident
+//   warp 3      relay    : waits for each chunk's tcgen05.commit mbarrier and releases the filter warps (named barriers)
 //   warps 4-7   convert  : staging -> scales / norms / bounds -> FP16 A image (2 stages)
 //   warps 8-19  epilogue : tcgen05.ld TMEM -> min tree + ambiguity masks per 32-code sub-chunk; three warps
 //                          per TMEM lane quarter split the columns, the owner merges and writes idx / histogram
@@ -65,6 +66,8 @@ constexpr int NUM_WARPS = GATHER_WARP0 + GATHER_WARPS;
 // (plus the z rows requested ahead of the codes) do not fit 80.  The trade must balance inside the CTA's own
 // allocation — setmaxnreg.inc only draws from what the CTA released: 128 * (48 + 80 + 112) + 384 * 80 = 61 440.
 constexpr int REGS_CTRL = 48, REGS_GATHER = 112;
+// streamed-codebook variant (ST): control 40, converter 64, gather 64, epilogue 104 (128 * (40 + 64 + 64) + 384 * 104 = 61 440)
+constexpr int REGS_ST_CTRL = 40, REGS_ST_SIDE = 64, REGS_ST_EPI = 104;
 constexpr int DSLICE = 64;                   // e_dim is contracted in slices of at most 64 columns
 // slice width: the whole row up to 64 columns, 64-column slices up to e_dim 256, 32-column slices for e_dim 512
 // (the resident A image of 128 x 528 halfs leaves room for only small staging / ring slots)
@@ -363,7 +366,17 @@ struct RowState {   // per (row, column subset) running result of the filter
                     // high half, odd columns in the low half, bit 15 - j/2 of a half <-> column j
   int col0;         // first code of that sub-chunk
   uint32_t cand;    // groups of sub-chunks holding a key within `band` of m1 (superset; always holds m1's own)
+  int ncand;        // list mode: entries pushed into `cand` since the last reset (more than three = overflow)
 };
+// Record that sub-chunk `gbit` held a key inside the band.  Mask mode: set its bit.  List mode: push its 10-bit entry
+// (newest in the low bits) and count; with more than three pushes the oldest entry has been shifted out and the
+// record becomes CAND_OVERFLOW when the tile is finished (filter_tile) — two predicated instructions per sub-chunk
+// instead of the branchy cand_union, which is kept for the once-per-tile merge of the warps' records.
+template <bool LIST>
+__device__ __forceinline__ void cand_push(RowState& st, uint32_t gbit) {
+  if (LIST) { st.cand = (st.cand << 10) | gbit; ++st.ncand; }
+  else st.cand |= gbit;
+}
 // code index of a set bit of the mask (for a decided row the only set bit is the minimum itself)
 __device__ __forceinline__ int row_state_col(const RowState& st) {
   const int zc = __clz(st.bits);                   // 0..15: even column 2*zc; 16..31: odd column 2*(zc-16)+1
@@ -422,26 +435,19 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
 //           the column of the minimum for a decided row (after the last reset the only key that was ever
 //           inside the band is the minimum itself), so no per-element index packing is needed.
 // ~3 issued instructions per element: 0.5 FMNMX3 (ALU) + 1 FFMA.SAT + 0.5 FFMA2 (FMA pipe).
-template <bool LIST>
-__device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uint32_t gbit, float band, float band_big, RowState& st) {
-  const float BIG = 1048576.f;
-  float key[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(v[j]);
+__device__ __forceinline__ float subchunk_min(const float (&key)[32]) {
   float a0 = min3f(key[0], key[1], key[2]), a1 = min3f(key[3], key[4], key[5]);
   float a2 = min3f(key[6], key[7], key[8]), a3 = min3f(key[9], key[10], key[11]);
   float a4 = min3f(key[12], key[13], key[14]), a5 = min3f(key[15], key[16], key[17]);
   float a6 = min3f(key[18], key[19], key[20]), a7 = min3f(key[21], key[22], key[23]);
   float a8 = min3f(key[24], key[25], key[26]), a9 = min3f(key[27], key[28], key[29]);
   a0 = min3f(a0, a1, a2); a3 = min3f(a3, a4, a5); a6 = min3f(a6, a7, a8); a9 = min3f(a9, key[30], key[31]);
-  // running minimum folded into the tree: m1n = min(sub-chunk minimum, previous minimum)
-  const float m1n = min3f(min3f(a0, a3, a6), a9, st.m1);
-  // An improvement by more than the band voids every earlier key exactly (cnt := -1 cancels the new
-  // minimum's own hit below); a smaller improvement (or none: 0) leaves the old minimum inside the band,
-  // which the new minimum's own hit accounts for.
-  if (st.m1 - m1n > band) { st.cnt = -1; st.cand = 0u; }
-  st.m1 = m1n;
-  const float TB = fmaf(m1n, BIG, band_big);   // == (m1 + band) * 2^20: scaling by a power of two commutes with the rounding
+  return fminf(min3f(a0, a3, a6), a9);
+}
+// indicator masks of "key < T" for the 32 keys of a sub-chunk (TB = T * 2^20): even columns in the high half,
+// odd columns in the low half, bit 15 - j/2 of a half <-> column j
+__device__ __forceinline__ uint32_t subchunk_bits(const float (&key)[32], float TB) {
+  const float BIG = 1048576.f;
   const uint64_t two = pack_f32x2(2.f, 2.f);
   // four independent Horner chains of 4 steps (columns 0-7, 8-15, 16-23, 24-31): short dependency chains
   uint64_t h0 = pack_f32x2(0.f, 0.f), h1 = h0, h2 = h0, h3 = h0;
@@ -458,9 +464,50 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
   float fe, fo;
   unpack_f32x2(acc2, fe, fo);
   // both masks in one integer: fe * 65536 + fo would need 32 mantissa bits, so the halves are converted separately
-  const uint32_t bits = ((uint32_t)__float2int_rn(fe) << 16) | (uint32_t)__float2int_rn(fo);
+  return ((uint32_t)__float2int_rn(fe) << 16) | (uint32_t)__float2int_rn(fo);
+}
+
+template <bool LIST>
+__device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uint32_t gbit, float band, float band_big, RowState& st) {
+  const float BIG = 1048576.f;
+  float key[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(v[j]);
+  // running minimum: m1n = min(sub-chunk minimum, previous minimum)
+  const float m1n = fminf(subchunk_min(key), st.m1);
+  // An improvement by more than the band voids every earlier key exactly (cnt := -1 cancels the new
+  // minimum's own hit below); a smaller improvement (or none: 0) leaves the old minimum inside the band,
+  // which the new minimum's own hit accounts for.
+  if (st.m1 - m1n > band) { st.cnt = -1; st.cand = 0u; st.ncand = 0; }
+  st.m1 = m1n;
+  const float TB = fmaf(m1n, BIG, band_big);   // == (m1 + band) * 2^20: scaling by a power of two commutes with the rounding
+  const uint32_t bits = subchunk_bits(key, TB);
   st.cnt += __popc(bits);
-  if (bits) { st.cand = cand_union<LIST>(st.cand, gbit); st.bits = bits; st.col0 = col0; }   // the position is decoded once per row
+  if (bits) { cand_push<LIST>(st, gbit); st.bits = bits; st.col0 = col0; }   // the position is decoded once per row
+}
+
+// Two sub-chunks at once (A before B in code order): the same result as two calls of filter_subchunk, written so
+// that the two min trees and the two indicator passes are independent instruction streams — a warp then fills the
+// fixed-latency gaps of one with the other (the streamed-codebook variant gives the epilogue warps the registers).
+template <bool LIST>
+__device__ __forceinline__ void filter_subchunk2(uint32_t (&va)[32], uint32_t (&vb)[32], int col_a, int col_b, uint32_t gbit_a, uint32_t gbit_b,
+                                                 float band, float band_big, RowState& st) {
+  const float BIG = 1048576.f;
+  float ka[32], kb[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { ka[j] = __uint_as_float(va[j]); kb[j] = __uint_as_float(vb[j]); }
+  const float m1a = fminf(subchunk_min(ka), st.m1);
+  const float m1b = fminf(subchunk_min(kb), m1a);
+  const bool reset_a = st.m1 - m1a > band, reset_b = m1a - m1b > band;
+  const uint32_t bits_a = subchunk_bits(ka, fmaf(m1a, BIG, band_big));
+  const uint32_t bits_b = subchunk_bits(kb, fmaf(m1b, BIG, band_big));
+  if (reset_a) { st.cnt = -1; st.cand = 0u; st.ncand = 0; }
+  st.cnt += __popc(bits_a);
+  if (bits_a) { cand_push<LIST>(st, gbit_a); st.bits = bits_a; st.col0 = col_a; }
+  if (reset_b) { st.cnt = -1; st.cand = 0u; st.ncand = 0; }
+  st.cnt += __popc(bits_b);
+  if (bits_b) { cand_push<LIST>(st, gbit_b); st.bits = bits_b; st.col0 = col_b; }
+  st.m1 = m1b;
 }
 
 // DT > 0: e_dim known at compile time (strides, trip counts and index masks become immediates and the
@@ -469,8 +516,11 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
 // CE: the converter warps join the filter as a fourth warp per TMEM lane quarter (streamed codebooks with a
 // double-buffered A image: a tile then has many accumulator chunks and the converters would idle for most of it;
 // with four warps per quarter every warp takes exactly two of a chunk's eight sub-chunks instead of 3 / 3 / 2).
-template <int DT, bool TRAIN, bool LIST, bool CE>
+// ST: variant for streamed codebooks (many accumulator chunks per tile): the converter and gather warps work once per
+// tile and can live with 64 registers, so the epilogue warps get 104 and filter two sub-chunks at a time.
+template <int DT, bool TRAIN, bool LIST, bool CE, bool ST>
 __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
+  static_assert(!(CE && ST), "the converter warps cannot hold the two-sub-chunk filter in 64 registers");
   constexpr int EPQX = CE ? EPQ + 1 : EPQ;       // filter warps per TMEM lane quarter
   constexpr int NB_ACC_THREADS = nb_acc_threads(EPQX), NB_ACC_HLP_THREADS = nb_acc_hlp_threads(EPQX), NB_FIN_THREADS = nb_fin_threads(EPQX);
   extern __shared__ __align__(128) uint8_t smem[];
@@ -524,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   // vq_tc_cand_gshift); list mode: sub-chunk index + 1.
   auto filter_tile = [&](int64_t it, uint32_t& q, int wq, int r, RowState& st, float& band) {
     const uint32_t lane_addr = (uint32_t)(r & ~31) << 16;
-    st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0; st.bits = 0u; st.col0 = 0; st.cand = 0u;
+    st.m1 = __uint_as_float(0x7f800000u); st.cnt = 0; st.bits = 0u; st.col0 = 0; st.cand = 0u; st.ncand = 0;
     float band_big = 0.f;
     const int sc0 = (wq + EPQX - 1) % EPQX;
     for (int c = 0; c < nchunks; ++c, ++q) {
@@ -543,6 +593,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const int col_end = c * 256 + n;
       uint32_t taddr = tmem_base + lane_addr + t * 256u + (uint32_t)sc0 * 32u;
       uint32_t gbit = LIST ? (uint32_t)(c * 8 + sc0 + 1) : 1u << (c * 8 + sc0);
+      if (ST) {
+        // two of my sub-chunks per step (both loads issued before either is consumed)
+#pragma unroll 1
+        for (; col + 32 * EPQX < col_end; col += 64 * EPQX, taddr += 64u * EPQX, gbit = LIST ? gbit + 2 * EPQX : gbit << (2 * EPQX)) {
+          uint32_t va[32], vb[32];
+          tc::tmem_ld32(taddr, va);
+          tc::tmem_ld32(taddr + 32u * EPQX, vb);
+          tmem_ld_wait_dep(va);
+          tmem_ld_wait_dep(vb);
+          filter_subchunk2<LIST>(va, vb, col, col + 32 * EPQX, gbit, LIST ? gbit + EPQX : gbit << EPQX, band, band_big, st);
+        }
+      }
 #pragma unroll 1
       for (; col < col_end; col += 32 * EPQX, taddr += 32u * EPQX, gbit = LIST ? gbit + EPQX : gbit << EPQX) {
         uint32_t v[32];
@@ -555,6 +617,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       if (wq == 1 && r < 32) TRACE(2, 1, c & 1);
       if ((int64_t)q + 2 < total_chunks) nb_arrive(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS);
     }
+    if (LIST && st.ncand > 3) st.cand = CAND_OVERFLOW;   // an entry was shifted out: the refine scans every code of this row
   };
   // a helper hands its partial result of the tile to the owner warp of the same rows (single slot per helper)
   auto helper_handoff = [&](int64_t it, int wq, int r, const RowState& st) {
@@ -569,7 +632,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   };
 
   if (warp < CONV_WARP0) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));   // whole warpgroup, before the roles split
+  if (ST) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ST_CTRL));
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));   // whole warpgroup, before the roles split
   if (warp == 0) {
     // ===================== producer: z tile (slices) -> staging ring =====================
     {
@@ -638,6 +702,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp; lane 0 issues) =====================
+    // (the completion relay described below now runs in warp 3)
     // In order per chunk: wait for the accumulator stage (named barrier, epilogue -> MMA), issue, wait for
     // the completion mbarrier of this chunk's tcgen05.commit and relay it to the 12 epilogue warps through a
     // named barrier, so that only this warp ever polls.  The next chunk is issued after the relay: with
@@ -705,11 +770,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
             __syncwarp();
           }
           TRACE(0, 2, c & 1);
-          wait_or_trap(BAR(B_ACC_FULL, t), (q >> 1) & 1u, err_out, ERR_ACC_FULL);
-          TRACE(0, 3, c & 1);
-          tc::tc_fence_before();
-          nb_arrive(NB_ACC_FULL_HLP + (int)t, NB_ACC_HLP_THREADS);
-          nb_arrive(NB_ACC_FULL_OWN + (int)t, NB_ACC_OWN_THREADS);
+          // (the completion of this chunk is awaited and relayed by warp 3, so that the next chunk's MMAs are issued
+          //  while these execute: measured at K = 16 384 the issuer warp spent ~155 instructions and the whole MMA
+          //  execution time per chunk in this loop, serially — it, not the filter, set the chunk period)
         }
       }
 #ifdef DVQ_TC_STATS
@@ -717,9 +780,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 #endif
       STAT_FLUSH(3, 1);
     }
-  }   // (warp 3 is the spare of the control warpgroup: nothing to do until the final barrier)
+  } else {
+    // ===================== relay (warp 3): tcgen05.commit mbarrier of a chunk -> named barriers of the filter warps =====================
+    // Only this warp polls the completion mbarrier; the filter warps sleep in bar.sync.  A stage's barrier cannot
+    // be committed again before this relay: the MMAs of chunk q + 2 wait for the filter warps to release the
+    // stage, and those wait for this relay of chunk q.
+    for (int64_t q = 0; q < total_chunks; ++q) {
+      const uint32_t t = (uint32_t)(q & 1);
+      wait_or_trap(BAR(B_ACC_FULL, t), (uint32_t)((q >> 1) & 1), err_out, ERR_ACC_FULL);
+      tc::tc_fence_before();
+      nb_arrive(NB_ACC_FULL_HLP + (int)t, NB_ACC_HLP_THREADS);
+      nb_arrive(NB_ACC_FULL_OWN + (int)t, NB_ACC_OWN_THREADS);
+    }
+  }
   } else if (warp < EPI_WARP0) {
     // ===================== converters: thread <-> tile row =====================
+    if (ST) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ST_SIDE));
     const int r = (warp - CONV_WARP0) * 32 + lane;
     const CbMeta cb = *p.cb;
     STAT_DECL(3);
@@ -858,6 +934,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     STAT_FLUSH(3, 4);
   } else if (warp < GATHER_WARP0) {
     // ===================== epilogue: TMEM -> (min, ambiguity) per row =====================
+    if (ST) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_ST_EPI));
     const int w = warp - EPI_WARP0;
     const int quarter = warp & 3;       // TMEM lanes this warp may access: 32*(warp_id % 4)
     const int wq = w >> 2;              // 0 = owner of these rows, 1..EPQ-1 = helpers (they split the columns)
@@ -933,7 +1010,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     STAT_FLUSH(5, 7);
   } else {
     // ===================== gather: z_q, idx, SSE, histogram for the decided rows =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_GATHER));
+    if (ST) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ST_SIDE));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_GATHER));
     const int gw = warp - GATHER_WARP0;
     int* shist = reinterpret_cast<int*>(smem + L.hist);
     const int nv = D / 4;                              // float4 slots per row (power of two)
@@ -949,8 +1027,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     const int nsteps = rows_per_warp / rps;            // row-steps per warp per tile (per part)
     const int rbase = gw * rows_per_warp + rsub;
     double sse_acc = 0.0;
-    constexpr bool PREFETCH_Z = true;                  // request the first batch's z rows before the codes arrive (needs ~16 more registers)
-    constexpr int UH = 4;                              // row-steps per batch; two batches in flight per lane (x2 loads in train mode)
+    constexpr bool PREFETCH_Z = !ST;                   // request the first batch's z rows before the codes arrive (needs ~16 more registers)
+    constexpr int UH = ST ? 2 : 4;                            // row-steps per batch; two batches in flight per lane (x2 loads in train mode)
     STAT_DECL(2);
 #ifdef DVQ_TC_STATS
     const long long g_t0 = clock64();
@@ -1159,21 +1237,30 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   const bool streamed = ((K + 255) / 256) * (int)L.ns > 2;
   const bool ce_ok = streamed && L.a_bufs == 2;
   const bool ce = ce_ok && (ce_env ? ce_env[0] == '1' : (L.ns == 1 && (K + 255) / 256 >= 16));
-#define DVQ_LAUNCH_TC(DT_, TR_, LS_, CE_)                                                                                   \
+#define DVQ_LAUNCH_TC(DT_, TR_, LS_, CE_, ST_)                                                                              \
   do {                                                                                                                 \
-    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<DT_, TR_, LS_, CE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    vq_tc_kernel<DT_, TR_, LS_, CE_><<<(unsigned)grid, NTHREADS, smem, s>>>(p);                                             \
+    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<DT_, TR_, LS_, CE_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    vq_tc_kernel<DT_, TR_, LS_, CE_, ST_><<<(unsigned)grid, NTHREADS, smem, s>>>(p);                                        \
   } while (0)
+#define DVQ_LAUNCH_TC_GENERIC(TR_, LS_)                                      \
+  do {                                                                       \
+    if (st) DVQ_LAUNCH_TC(0, TR_, LS_, false, true);                         \
+    else if (ce) DVQ_LAUNCH_TC(0, TR_, LS_, true, false);                    \
+    else DVQ_LAUNCH_TC(0, TR_, LS_, false, false);                           \
+  } while (0)
+  // two-sub-chunk filter with the epilogue-heavy register split (DVQ_TC_ST=1; streamed codebooks only).  Measured
+  // within +-2 % of the default at every K >= 2048 shape of the sweep, so it is not selected automatically.
+  static const char* st_env = getenv("DVQ_TC_ST");
+  const bool st = streamed && st_env && st_env[0] == '1';
   const bool list = p.cand_gshift < 0;
   if (D == 64 && !list && !streamed) {
-    if (train) DVQ_LAUNCH_TC(64, true, false, false); else DVQ_LAUNCH_TC(64, false, false, false);
+    if (train) DVQ_LAUNCH_TC(64, true, false, false, false); else DVQ_LAUNCH_TC(64, false, false, false, false);
   } else if (!list) {
-    if (ce) { if (train) DVQ_LAUNCH_TC(0, true, false, true); else DVQ_LAUNCH_TC(0, false, false, true); }
-    else { if (train) DVQ_LAUNCH_TC(0, true, false, false); else DVQ_LAUNCH_TC(0, false, false, false); }
+    if (train) DVQ_LAUNCH_TC_GENERIC(true, false); else DVQ_LAUNCH_TC_GENERIC(false, false);
   } else {
-    if (ce) { if (train) DVQ_LAUNCH_TC(0, true, true, true); else DVQ_LAUNCH_TC(0, false, true, true); }
-    else { if (train) DVQ_LAUNCH_TC(0, true, true, false); else DVQ_LAUNCH_TC(0, false, true, false); }
+    if (train) DVQ_LAUNCH_TC_GENERIC(true, true); else DVQ_LAUNCH_TC_GENERIC(false, true);
   }
+#undef DVQ_LAUNCH_TC_GENERIC
 #undef DVQ_LAUNCH_TC
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch();
