@@ -473,8 +473,18 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
   float key[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(v[j]);
+  const float m = subchunk_min(key);
+  if (LIST) {
+    // Large codebooks: after the first few dozen sub-chunks of a row most sub-chunks hold no key below the running
+    // threshold (the chance is ~1/j for the j-th), and then nothing changes — no new minimum, no indicator bit.  The
+    // test applies the indicator arithmetic itself to the sub-chunk minimum (monotone in the key, so a zero here means
+    // 32 zeros below; any new minimum lies below the threshold and gives 1); when no row of the warp needs it the
+    // indicator pass and the state update (two thirds of the instructions) are skipped.
+    const bool need = fma_sat(m, -BIG, fmaf(st.m1, BIG, band_big)) != 0.f;
+    if (!__any_sync(0xffffffffu, need)) return;
+  }
   // running minimum: m1n = min(sub-chunk minimum, previous minimum)
-  const float m1n = fminf(subchunk_min(key), st.m1);
+  const float m1n = fminf(m, st.m1);
   // An improvement by more than the band voids every earlier key exactly (cnt := -1 cancels the new
   // minimum's own hit below); a smaller improvement (or none: 0) leaves the old minimum inside the band,
   // which the new minimum's own hit accounts for.
