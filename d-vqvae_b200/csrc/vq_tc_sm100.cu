@@ -110,14 +110,35 @@ struct TcParams {
   int64_t ntiles;
 };
 
+constexpr int MAX_BSLOTS = 4;           // ring slots of the streamed codebook image
+
 struct SmemLayout {
   uint32_t bimg, a_img[2], stage[2], meta, fin, sidx, hist, total;
-  uint32_t bimg_bytes, a_bytes, stage_bytes;   // bimg_bytes: the 2-slot codebook ring in shared memory
+  uint32_t bimg_bytes, a_bytes, stage_bytes;   // bimg_bytes: the codebook ring (nslots slots) in shared memory
   uint32_t bchunk_bytes, hist_in_smem;           // one ring slot: (256 codes) x (one e_dim slice + the fold columns)
   uint32_t ns, ds, a_bufs, bslice_bytes;         // e_dim = ns slices of ds columns; a slice without the fold columns
+  uint32_t nslots, nstage;                       // ring slots (2..MAX_BSLOTS), z staging slots (1..2)
 };
 
 constexpr uint32_t SMEM_LIMIT = 227u * 1024u - 640u;   // dynamic shared memory budget (alignment slack + static barriers)
+
+__host__ __device__ inline uint32_t smem_place(SmemLayout& L, int K) {
+  uint32_t off = 0;
+  L.bimg_bytes = L.nslots * L.bchunk_bytes;
+  L.bimg = off; off += (L.bimg_bytes + 127u) & ~127u;
+  L.a_img[0] = off; off += (L.a_bytes + 127u) & ~127u;
+  L.a_img[1] = L.a_bufs == 2 ? off : L.a_img[0];
+  if (L.a_bufs == 2) off += (L.a_bytes + 127u) & ~127u;
+  L.stage[0] = off; off += L.stage_bytes;
+  L.stage[1] = L.nstage == 2 ? off : L.stage[0];
+  if (L.nstage == 2) off += L.stage_bytes;
+  L.meta = off; off += META_SLOTS * TM * 4;
+  L.fin = off; off += EPQ * TM * 16;         // up to EPQ helper warps (EPQ + 1 warps per quarter when the converters join) x (key, col, cnt, cand); single slot
+  L.sidx = off; off += 2 * TM * 4;      // 2 slots of the hand-off word (code offset | undecided flag + candidates)
+  L.hist = off; off += L.hist_in_smem ? (uint32_t)K * 4 : 0u;
+  L.total = off;
+  return off;
+}
 
 __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   SmemLayout L;
@@ -126,28 +147,42 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   const uint32_t kc_s = L.ds / 8, kc_a = (uint32_t)((USE_ZL ? 2 : 1) * D + 16) / 8;
   L.bslice_bytes = kc_s * 256u * 16u;
   L.bchunk_bytes = (kc_s + 2u) * 256u * 16u;
-  L.bimg_bytes = 2u * L.bchunk_bytes;
   L.a_bytes = kc_a * A_CHUNK_BYTES;
   L.stage_bytes = (uint32_t)TM * L.ds * 4;
-  // preference order when shared memory is short: drop the shared-memory histogram (global atomics), then the
-  // second A image (the converters then wait for the previous tile's MMAs)
-  for (int attempt = 0; attempt < 3; ++attempt) {
-    L.hist_in_smem = (K <= 512 && attempt == 0) ? 1u : 0u;   // larger histograms go straight to global atomics
-    L.a_bufs = attempt < 2 ? 2u : 1u;
-    uint32_t off = 0;
-    L.bimg = off; off += (L.bimg_bytes + 127u) & ~127u;
-    L.a_img[0] = off; off += (L.a_bytes + 127u) & ~127u;
-    L.a_img[1] = L.a_bufs == 2 ? off : L.a_img[0];
-    if (L.a_bufs == 2) off += (L.a_bytes + 127u) & ~127u;
-    L.stage[0] = off; off += L.stage_bytes;
-    L.stage[1] = off; off += L.stage_bytes;
-    L.meta = off; off += META_SLOTS * TM * 4;
-    L.fin = off; off += EPQ * TM * 16;         // up to EPQ helper warps (EPQ + 1 warps per quarter when the converters join) x (key, col, cnt, cand); single slot
-    L.sidx = off; off += 2 * TM * 4;      // 2 slots of the hand-off word (code offset | undecided flag + candidates)
-    L.hist = off; off += L.hist_in_smem ? (uint32_t)K * 4 : 0u;
-    L.total = off;
-    if (L.total <= SMEM_LIMIT) break;
+  const uint32_t nchunks = (uint32_t)(K + 255) / 256;
+  if (nchunks * L.ns <= 2) {
+    // resident operand image (two slots hold it for the life of the CTA).  Preference order when shared memory is
+    // short: drop the shared-memory histogram (global atomics), then the second A image (the converters then
+    // wait for the previous tile's MMAs)
+    L.nslots = 2; L.nstage = 2;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      L.hist_in_smem = (K <= 512 && attempt == 0) ? 1u : 0u;   // larger histograms go straight to global atomics
+      L.a_bufs = attempt < 2 ? 2u : 1u;
+      if (smem_place(L, K) <= SMEM_LIMIT) break;
+    }
+    return L;
   }
+  // streamed image: blocks in flight hide the L2 latency.  Measured (N = 16.8 M): a third ring slot is worth +7 % at
+  // e_dim 128, K = 16 384 even at the price of a single A image and a single staging slot, but with a single A
+  // image K = 2048 / 4096 lose 10-17 % (the MMAs stall while each tile is converted).  Hence: from 32 chunks per
+  // tile on the third slot comes first; from 8 chunks on it only replaces the second z staging slot (a tile lasts
+  // long enough for one); below that the layout of the resident case is kept.
+  L.hist_in_smem = 0u;
+  uint32_t best_score = 0, best_a = 1, best_st = 1, best_sl = 2;
+  for (uint32_t a = 2; a >= 1; --a)
+    for (uint32_t st = 2; st >= 1; --st)
+      for (uint32_t sl = MAX_BSLOTS; sl >= 2; --sl) {
+        L.a_bufs = a; L.nstage = st; L.nslots = sl;
+        if (smem_place(L, K) > SMEM_LIMIT) continue;
+        const uint32_t sl3 = sl < 3u ? sl : 3u;
+        const uint32_t score = nchunks >= 32 ? sl3 * 100u + a * 10u + st + sl
+                             : nchunks >= 8  ? a * 100u + sl3 * 10u + st
+                                             : a * 100u + st * 10u + sl;
+        if (score > best_score) { best_score = score; best_a = a; best_st = st; best_sl = sl; }
+        break;   // the largest ring for this (a, st)
+      }
+  L.a_bufs = best_a; L.nstage = best_st; L.nslots = best_sl;
+  smem_place(L, K);   // (total > SMEM_LIMIT if nothing fits: vq_tc_supported rejects the shape)
   return L;
 }
 
@@ -340,7 +375,7 @@ __device__ __forceinline__ float half_minus_float(uint32_t h16, float a) {
 }
 
 // All barriers live in one shared struct so that a site addresses its barrier as base + immediate.
-enum BarId { B_STAGE_FULL = 0, B_STAGE_EMPTY = 2, B_ACC_FULL = 4, B_B_FULL = 6, B_B_EMPTY = 8, B_A_EMPTY = 10, NBARS = 12 };
+enum BarId { B_STAGE_FULL = 0, B_STAGE_EMPTY = 2, B_ACC_FULL = 4, B_A_EMPTY = 6, B_B_FULL = 8, B_B_EMPTY = 8 + MAX_BSLOTS, NBARS = 8 + 2 * MAX_BSLOTS };
 // named barrier ids (0 is __syncthreads).  The accumulator-full relay has one barrier per (stage, warp group):
 // the helper warps of a tile must not wait for the owner warps, which are still merging / writing the previous
 // tile when the helpers are ready for the next one.
@@ -559,9 +594,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       tc::mbar_init(&ctl.bars[B_STAGE_FULL + i], 1);
       tc::mbar_init(&ctl.bars[B_STAGE_EMPTY + i], 4);    // one arrival per converter warp
       tc::mbar_init(&ctl.bars[B_ACC_FULL + i], 1);       // tcgen05.commit
+      tc::mbar_init(&ctl.bars[B_A_EMPTY + i], 1);        // tcgen05.commit
+    }
+    for (int i = 0; i < MAX_BSLOTS; ++i) {
       tc::mbar_init(&ctl.bars[B_B_FULL + i], 1);
       tc::mbar_init(&ctl.bars[B_B_EMPTY + i], 1);
-      tc::mbar_init(&ctl.bars[B_A_EMPTY + i], 1);        // tcgen05.commit
     }
     tc::fence_barrier_init();
   }
@@ -665,8 +702,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         const int64_t row0 = tile * TM;
         const int rows = (int)min((int64_t)TM, p.N - row0);
         for (int sl = 0; sl < ns; ++sl, ++js) {
-          const int s = (int)(js & 1u);
-          const uint32_t ph = (js >> 1) & 1u;
+          const int s = L.nstage == 2 ? (int)(js & 1u) : 0;
+          const uint32_t ph = L.nstage == 2 ? (js >> 1) & 1u : js & 1u;
           { STAT_T0(); wait_or_trap(BAR(B_STAGE_EMPTY, s), ph ^ 1u, err_out, ERR_STAGE_EMPTY); STAT_ADD(0); }
           if (ns == 1) {
             if (lane == 0) {   // the whole tile is one contiguous block
@@ -693,12 +730,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
   } else if (warp == BLOAD_WARP) {
     // ===================== codebook streamer: (chunk, slice) blocks of the operand image from L2 -> 2-slot ring =====================
     if (lane == 0 && !resident) {
-      uint32_t qb = 0;
+      uint32_t slot = 0, ph = 0;   // ring position: slot index and the phase bit of its barriers
       for (int64_t it = 0; it < my_tiles; ++it) {
         for (int c = 0; c < nchunks; ++c) {
-          for (int sl = 0; sl < ns; ++sl, ++qb) {
-            const uint32_t slot = qb & 1u;
-            wait_or_trap(BAR(B_B_EMPTY, slot), ((qb >> 1) & 1u) ^ 1u, err_out, ERR_B_FULL);
+          for (int sl = 0; sl < ns; ++sl) {
+            wait_or_trap(BAR(B_B_EMPTY, slot), ph ^ 1u, err_out, ERR_B_FULL);
             const uint32_t bytes = sl == ns - 1 ? L.bchunk_bytes : L.bslice_bytes;   // the fold columns ride with the last slice
             const uint8_t* src = p.bimg + (size_t)(c * ns + sl) * L.bchunk_bytes;
             tc::mbar_arrive_expect_tx_a(BAR(B_B_FULL, slot), bytes);
@@ -706,6 +742,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
               const uint32_t n = min(16384u, bytes - off);
               tc::bulk_g2s_a(smem0 + L.bimg + slot * L.bchunk_bytes + off, src + off, n, BAR(B_B_FULL, slot));
             }
+            if (++slot == L.nslots) { slot = 0; ph ^= 1u; }
           }
         }
       }
@@ -732,7 +769,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       const uint64_t a_desc1 = tc::make_smem_desc(sbase + L.a_img[1], a_lbo, a_sbo);
       const uint64_t b_desc0 = tc::make_smem_desc(sbase + L.bimg, b_lbo, b_sbo);
       const uint32_t barbase = tc::smem_u32(ctl.bars);
-      uint32_t q = 0, qb = 0;   // accumulator chunks / operand blocks consumed so far
+      uint32_t q = 0;           // accumulator chunks consumed so far
+      uint32_t rslot = 0, rph = 0;   // ring position of the next operand block (slot, phase bit)
       STAT_DECL(3);
 #ifdef DVQ_TC_STATS
       const long long mma_t0 = clock64();
@@ -749,9 +787,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
           const int n = min(256, K - c * 256);
           const uint32_t idesc = tc::make_idesc_f16(128, n, 0);
           const uint32_t d_tmem = tmem_base + t * 256u;
-          for (int sl = 0; sl < ns; ++sl, ++qb) {
-            const uint32_t bslot = resident ? (uint32_t)(c * ns + sl) : (qb & 1u);
-            if (!resident) wait_or_trap(BAR(B_B_FULL, bslot), (qb >> 1) & 1u, err_out, ERR_B_FULL);
+          for (int sl = 0; sl < ns; ++sl) {
+            const uint32_t bslot = resident ? (uint32_t)(c * ns + sl) : rslot;
+            if (!resident) wait_or_trap(BAR(B_B_FULL, bslot), rph, err_out, ERR_B_FULL);
             tc::tc_fence_after();
             if (tc::elect_one()) {
               const uint64_t bc = b_desc0 + (uint64_t)((bslot * L.bchunk_bytes) >> 4);
@@ -777,6 +815,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
               }
               if (!resident) tc::umma_commit_a(barbase + 8u * (B_B_EMPTY + bslot));   // ring slot free once these MMAs have read it
             }
+            if (!resident && ++rslot == L.nslots) { rslot = 0; rph ^= 1u; }
             __syncwarp();
           }
           TRACE(0, 2, c & 1);
@@ -824,8 +863,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       float nsq = 0.f;
       bool finite = true;
       if (ns == 1) {
-        const int s = (int)(js & 1u);
-        { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), (js >> 1) & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
+        const int s = L.nstage == 2 ? (int)(js & 1u) : 0;
+        { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), L.nstage == 2 ? (js >> 1) & 1u : js & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
         if (warp == CONV_WARP0) TRACE(3, 0, 0);
         const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nvs;
         if (r < rows) {
@@ -869,8 +908,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       // convert slice by slice and write the A image
       uint8_t* aimg = smem + L.a_img[a] + (r >> 3) * 128 + (r & 7) * 16;
       for (int sl = 0; sl < ns; ++sl, ++js) {
-        const int s = (int)(js & 1u);
-        if (ns > 1) { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), (js >> 1) & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
+        const int s = L.nstage == 2 ? (int)(js & 1u) : 0;
+        if (ns > 1) { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), L.nstage == 2 ? (js >> 1) & 1u : js & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
         const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nvs;
         uint8_t* aslice = aimg + (size_t)(sl * (nvs / 2)) * A_CHUNK_BYTES;
         for (int i = 0; i < nvs / 2; ++i) {
@@ -1238,15 +1277,12 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   p.ntiles = (N + TM - 1) / TM;
   const size_t smem = L.total + 128;
   const int64_t grid = p.ntiles < dp.sm_count ? p.ntiles : dp.sm_count;
-  // Converters join the filter as a fourth warp per TMEM lane quarter where that was measured to pay: single-slice
-  // shapes (e_dim <= 64) with at least 16 accumulator chunks per tile (+4 % at K >= 4096; with few chunks the
-  // serialisation against the conversion costs more than the extra warp gives, and the sliced shapes are bound by
-  // streaming the operand blocks, not by the filter).  Needs a streamed codebook and a double-buffered A image.
-  // DVQ_TC_CE=0 / 1 forces it off / on where possible (A/B runs).
+  // Converters join the filter as a fourth warp per TMEM lane quarter (DVQ_TC_CE=1; needs a streamed codebook and a
+  // double-buffered A image).  It paid +4 % at e_dim 64, K >= 4096 while the filter was the bound; with the list-mode
+  // early-out the filter is cheap and the variant is 5 % behind the default there, so it is not selected automatically.
   static const char* ce_env = getenv("DVQ_TC_CE");
   const bool streamed = ((K + 255) / 256) * (int)L.ns > 2;
-  const bool ce_ok = streamed && L.a_bufs == 2;
-  const bool ce = ce_ok && (ce_env ? ce_env[0] == '1' : (L.ns == 1 && (K + 255) / 256 >= 16));
+  const bool ce = streamed && L.a_bufs == 2 && ce_env && ce_env[0] == '1';
 #define DVQ_LAUNCH_TC(DT_, TR_, LS_, CE_, ST_)                                                                              \
   do {                                                                                                                 \
     DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<DT_, TR_, LS_, CE_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
