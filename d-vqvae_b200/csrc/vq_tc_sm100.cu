@@ -819,9 +819,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
             __syncwarp();
           }
           TRACE(0, 2, c & 1);
-          // (the completion of this chunk is awaited and relayed by warp 3, so that the next chunk's MMAs are issued
-          //  while these execute: measured at K = 16 384 the issuer warp spent ~155 instructions and the whole MMA
-          //  execution time per chunk in this loop, serially — it, not the filter, set the chunk period)
+          // Streamed codebooks: the completion of this chunk is awaited and relayed by warp 3, so that the next
+          // chunk's MMAs are issued while these execute (+2-3 % at K = 16 384).  Resident image (two chunks per
+          // tile): this warp relays itself — the extra hop measured ~1.5 % slower there.
+          if (resident) {
+            wait_or_trap(BAR(B_ACC_FULL, t), (q >> 1) & 1u, err_out, ERR_ACC_FULL);
+            TRACE(0, 3, c & 1);
+            tc::tc_fence_before();
+            nb_arrive(NB_ACC_FULL_HLP + (int)t, NB_ACC_HLP_THREADS);
+            nb_arrive(NB_ACC_FULL_OWN + (int)t, NB_ACC_OWN_THREADS);
+          }
         }
       }
 #ifdef DVQ_TC_STATS
@@ -830,11 +837,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       STAT_FLUSH(3, 1);
     }
   } else {
-    // ===================== relay (warp 3): tcgen05.commit mbarrier of a chunk -> named barriers of the filter warps =====================
+    // ===================== relay (warp 3, streamed codebooks): tcgen05.commit mbarrier of a chunk -> named barriers of the filter warps =====================
     // Only this warp polls the completion mbarrier; the filter warps sleep in bar.sync.  A stage's barrier cannot
     // be committed again before this relay: the MMAs of chunk q + 2 wait for the filter warps to release the
     // stage, and those wait for this relay of chunk q.
-    for (int64_t q = 0; q < total_chunks; ++q) {
+    for (int64_t q = 0; q < (resident ? 0 : total_chunks); ++q) {
       const uint32_t t = (uint32_t)(q & 1);
       wait_or_trap(BAR(B_ACC_FULL, t), (uint32_t)((q >> 1) & 1), err_out, ERR_ACC_FULL);
       tc::tc_fence_before();
