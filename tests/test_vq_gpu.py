@@ -334,3 +334,46 @@ def test_refine_variants_give_identical_results(K, D):
         assert rel_err(res[name][3], res["per_row"][3]) < 1e-7 and rel_err(res[name][4], res["per_row"][4]) < 1e-7
     n_mis, n_bad, worst = vo.allowed_index_mismatch(z, E, res["binned"][0], res["simt"][0])
     assert n_bad == 0, (n_mis, worst)
+
+
+_VARIANT_SNIPPET = r"""
+import os, sys
+import numpy as np, torch
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "d-vqvae_b200"))
+import dvq
+from dvq import _cabi
+from oracle import vq_oracle as vo
+for K, D in ((4096, 64), (2048, 32), (1024, 128)):
+    N = 30000 + 19
+    E = vo.default_codebook(K, D, 51); z = vo.normal_latents(N, D, 52)
+    z[::199] = 0.0
+    out = {}
+    for name, path in (("simt", _cabi.DVQ_PATH_SIMT), ("tc", _cabi.DVQ_PATH_TC)):
+        m = dvq.VectorQuantizer(K, D, 0.25, 1.0).cuda(); m.path = path; m.onehot_limit_bytes = 0
+        with torch.no_grad():
+            m.embedding.weight.copy_(torch.from_numpy(E))
+            loss, zq, ppl, _, idx = m(torch.from_numpy(z).cuda(), True)
+        assert m.last_counters(N)[1] == 0
+        out[name] = (idx.cpu().numpy().reshape(-1), zq.cpu().numpy().view(np.uint32), loss.item())
+    n_mis, n_bad, worst = vo.allowed_index_mismatch(z, E, out["tc"][0], out["simt"][0])
+    assert n_bad == 0, (K, D, n_mis, worst)
+    same = out["tc"][0] == out["simt"][0]
+    assert np.array_equal(out["tc"][1][same], out["simt"][1][same])
+    assert abs(out["tc"][2] - out["simt"][2]) <= 1e-5 * abs(out["simt"][2])
+print("VARIANT_OK")
+"""
+
+
+@pytest.mark.parametrize("env", [{"DVQ_TC_CE": "1"}, {"DVQ_TC_ST": "1"}], ids=["converters_join_filter", "two_subchunk_filter"])
+def test_streamed_kernel_variants_behind_env_switches(env):
+    """The streamed-codebook kernel has two optional variants selected by environment switches that are read once
+    per process (DVQ_TC_CE: the converter warps filter as a fourth warp per TMEM lane quarter; DVQ_TC_ST: epilogue
+    warps with 104 registers filter two sub-chunks per step).  Each must agree with the all-FP32 kernel under the
+    same parity rule as the default variant; a fresh interpreter per variant."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET, root], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "VARIANT_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
