@@ -26,7 +26,7 @@
 //   warp 0      producer : cp.async.bulk (TMA engine) z tile fp32 -> staging ring (2 x 128 x D x 4 B)
 //   warp 1      MMA      : one elected lane issues tcgen05.mma from uniform-register descriptors; the warp
 //                          then waits for the chunk's commit mbarrier and relays it on named barriers
-//   warp 2      streamer : codebook chunks -> 2-slot ring when the operand image is not resident
+//   warp 2      streamer : codebook chunks -> ring of 2-3 slots when the operand image is not resident
 //   warp 3      relay    : waits for each chunk's tcgen05.commit mbarrier and releases the filter warps (named barriers)
 //   warps 4-7   convert  : staging -> scales / norms / bounds -> FP16 A image (2 stages)
 //   warps 8-19  epilogue : tcgen05.ld TMEM -> min tree + ambiguity masks per 32-code sub-chunk; three warps
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       STAT_FLUSH(1, 0);
     }
   } else if (warp == BLOAD_WARP) {
-    // ===================== codebook streamer: (chunk, slice) blocks of the operand image from L2 -> 2-slot ring =====================
+    // ===================== codebook streamer: (chunk, slice) blocks of the operand image from L2 -> ring of L.nslots slots =====================
     if (lane == 0 && !resident) {
       uint32_t slot = 0, ph = 0;   // ring position: slot index and the phase bit of its barriers
       for (int64_t it = 0; it < my_tiles; ++it) {
