@@ -117,6 +117,13 @@ int dvq_vq_set_refine(int mode, long long pair_cap) {
   return DVQ_OK;
 }
 
+int dvq_debug_tc_layout(int K, int D, int* out8) {
+  if (!out8) return fail(DVQ_ERR_BAD_ARG, "out8 is NULL");
+  if (K <= 0 || D <= 0) return fail(DVQ_ERR_BAD_SHAPE, "need K > 0, D > 0");
+  vq_tc_layout_info(K, D, out8);
+  return DVQ_OK;
+}
+
 int dvq_profile_enable(int on) {
   g_prof_on = on != 0;
   for (int i = 0; i < kStages; ++i) g_prof_n[i] = 0;

@@ -59,6 +59,7 @@ int launch_vq_simt(const float* z, const float* E, const float* ee, int64_t N, i
 
 // tcgen05 filter kernel (vq_tc_sm100.cu); supported(K,D) says whether the shape is handled.
 bool vq_tc_supported(int64_t N, int K, int D);
+void vq_tc_layout_info(int K, int D, int* out8);   // dvq_debug_tc_layout
 size_t vq_tc_operand_bytes(int K, int D);
 size_t vq_tc_rownorm_bytes(int64_t N, int D);
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,

@@ -1242,6 +1242,16 @@ bool vq_tc_supported(int64_t N, int K, int D) {
   return smem_layout(K, D).total <= SMEM_LIMIT;
 }
 
+void vq_tc_layout_info(int K, int D, int* out8) {
+  const bool shape_ok = D >= 16 && D <= 512 && (D & (D - 1)) == 0 && K % 32 == 0 && K >= 32 && K <= 32704;
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (!shape_ok) return;
+  const SmemLayout L = smem_layout(K, D);
+  out8[0] = L.total <= SMEM_LIMIT ? 1 : 0;
+  out8[1] = (int)L.ds; out8[2] = (int)L.ns; out8[3] = (int)L.a_bufs; out8[4] = (int)L.nslots; out8[5] = (int)L.nstage;
+  out8[6] = (int)L.total + 128; out8[7] = (int)L.hist_in_smem;
+}
+
 int vq_tc_cand_gshift(int K) {   // 31 candidate bits (bit 31 is the "undecided" flag of the hand-off word), one per 32-code sub-chunk
   return K <= 992 ? 0 : -1;      // -1 = list mode: up to three exact sub-chunk indices instead of a mask
 }

@@ -74,6 +74,12 @@ DVQ_API int dvq_profile_mean(float* ms, int* count, int n);
  * hand-back to the per-row kernel, <= 0 restores the default.  Process-wide. */
 DVQ_API int dvq_vq_set_refine(int mode, long long pair_cap);
 
+/* Diagnostic (host-only, no GPU needed): the shared-memory plan the tcgen05 VQ kernel would use for a codebook
+ * shape.  out8 = { handled by the tensor-core path (0/1), e_dim slice width, slices per row, A images (1-2),
+ * operand ring slots (2-4), z staging slots (1-2), dynamic shared memory in bytes, histogram kept in shared
+ * memory (0/1) }.  Used by tests/test_cabi_symbols.py to pin the per-shape choices. */
+DVQ_API int dvq_debug_tc_layout(int K, int D, int* out8);
+
 /* Diagnostic used by tests/test_tc_probe_gpu.py: run `ksteps` tcgen05.mma (M=128, N=n_cols,
  * kind::f16) on caller-built shared-memory operand images and dump the [128,n_cols] fp32
  * accumulator.  strides = {a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep} in bytes; *err (device

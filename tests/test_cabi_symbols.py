@@ -104,3 +104,32 @@ def test_bn_fold_matches_oracle_math():
     ref = po._bn_eval(po._conv1x1(x, sd["conv2.weight"], sd["conv2.bias"]), sd, "bn2")
     got = np.einsum("oc,bcp->bop", w.numpy(), x) + b.numpy()[None, :, None]
     assert np.abs(got - ref).max() < 1e-5
+
+
+def test_tc_shared_memory_plan_per_shape():
+    """Host-only view of the tcgen05 VQ kernel's shared-memory plan (dvq_debug_tc_layout): every shape of the
+    BASELINE sweep fits the 227 KB budget, and the per-shape choices that were measured on the GPU are pinned —
+    resident image with a shared-memory histogram at config 2; a third ring slot instead of the second z staging slot
+    from 8 chunks per tile on (e_dim 64); at e_dim 128 the third slot replaces the second A image only from 32
+    chunks per tile on (with a single A image K = 2048 / 4096 measured 10-17 % slower)."""
+    from dvq import _cabi
+
+    def plan(K, D):
+        out = (ctypes.c_int * 8)()
+        _cabi.check(_cabi.lib.dvq_debug_tc_layout(K, D, out), "dvq_debug_tc_layout")
+        return dict(zip(("ok", "ds", "ns", "a_bufs", "nslots", "nstage", "bytes", "hist"), list(out)))
+
+    for K in (512, 1024, 2048, 4096, 8192, 16384):
+        for D in (16, 32, 64, 128, 256, 512):
+            p = plan(K, D)
+            assert p["ok"] == 1 and p["bytes"] <= 227 * 1024, (K, D, p)
+            assert p["ds"] * p["ns"] == D and 2 <= p["nslots"] <= 4 and 1 <= p["nstage"] <= 2 and 1 <= p["a_bufs"] <= 2
+    assert plan(512, 64) == dict(ok=1, ds=64, ns=1, a_bufs=2, nslots=2, nstage=2, bytes=plan(512, 64)["bytes"], hist=1)
+    assert (plan(1024, 64)["nslots"], plan(1024, 64)["nstage"], plan(1024, 64)["a_bufs"]) == (2, 2, 2)
+    for K in (2048, 4096, 16384):
+        assert (plan(K, 64)["nslots"], plan(K, 64)["nstage"], plan(K, 64)["a_bufs"]) == (3, 1, 2)
+    assert (plan(4096, 128)["nslots"], plan(4096, 128)["a_bufs"]) == (2, 2)
+    assert (plan(16384, 128)["nslots"], plan(16384, 128)["a_bufs"], plan(16384, 128)["nstage"]) == (3, 1, 1)
+    assert plan(16384, 256)["a_bufs"] == 1 and plan(16384, 512)["ds"] == 32
+    # shapes the tensor-core path does not take
+    assert plan(500, 64)["ok"] == 0 and plan(512, 48)["ok"] == 0 and plan(32768, 64)["ok"] == 0
