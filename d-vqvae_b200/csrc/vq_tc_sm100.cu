@@ -51,7 +51,7 @@ namespace {
 constexpr int TM = 128;                 // rows per tile
 constexpr int A_CHUNK_BYTES = TM * 16 + 32;  // one 8-wide k-chunk of the A image (+32 B: bank spreading)
 // Warp roles are laid out in aligned groups of four (warpgroups) so that a group can resize its register
-// allocation with setmaxnreg: warps 0-3 producer / MMA issuer / codebook streamer / spare, 4-7 converters,
+// allocation with setmaxnreg: warps 0-3 producer / MMA issuer / codebook streamer / completion relay, 4-7 converters,
 // 8-19 epilogue (three warpgroups: one warp per TMEM lane quarter each), 20-23 gather.
 constexpr int BLOAD_WARP = 2;                // codebook streamer (active when the image is not resident)
 constexpr int CONV_WARP0 = 4;
