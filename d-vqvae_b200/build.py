@@ -15,12 +15,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "dvq", "libdvq_sm100.so")
+# DVQ_BUILD_TAG=<tag> (with DVQ_CFLAGS="-D..." for experiment switches) builds a side-by-side variant
+# libdvq_sm100_<tag>.so that `DVQ_LIB=...` selects at import time; the default build has no tag.
+TAG = os.environ.get("DVQ_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "dvq", "libdvq_sm100" + ("_" + TAG if TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-         "-I", os.path.join(ROOT, "include"), "-I", CSRC] + (["-DDVQ_TC_STATS"] if os.environ.get("DVQ_TC_STATS") else [])
+         "-I", os.path.join(ROOT, "include"), "-I", CSRC] + (["-DDVQ_TC_STATS"] if os.environ.get("DVQ_TC_STATS") else []) + os.environ.get("DVQ_CFLAGS", "").split()
 
 
 def _sources():
