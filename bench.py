@@ -18,6 +18,10 @@ Weak scaling: every rank holds its own 4M-row shard, codebook replicated, one al
            around that kernel inside the library on the launching stream
   cpu_baseline  the reference's torch CPU op sequence (oracle/ref_port_torch.py, kind "port")
            on a bounded sample of the same workload, all host threads
+  secondary  driver-timed lines for the other BASELINE configs (each with its own roofline fraction): the config-4
+           corner K = 16384, e_dim 128 (16 777 216 latents in total, sharded over the GPUs), the PointNet encoder
+           (C = 4, P = 3000, 4096 clouds per GPU, tcgen05 path) and grasp generation (config 3 / 5: batch 4096 per
+           GPU, PixelCNN prior); whole-job aggregates, max-over-ranks time.  --no-secondary skips them.
 """
 from __future__ import annotations
 
@@ -50,8 +54,37 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 0.0)), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+        return (float(d["hbm_gbs"]), float(d.get("bf16_tflops", 0.0)), "measured (MEASURED_PEAKS.json)",
+                float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 0.0))))
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)", 1590.0
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process (and therefore the pinned host buffers it first-touches) to the CPU cores of the NUMA node
+    the GPU hangs off, so that the host-buffer (e2e) leg of every rank uses its own socket's memory controllers and
+    PCIe root instead of node 0.  Returns a description for the JSON line; a no-op where sysfs has no NUMA data."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                # nvml prints a 32-bit PCI domain, sysfs a 16-bit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for %s" % bus}
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"numa_node": node, "note": "no allowed core on that node"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cores": len(allowed)}
+    except Exception as e:                              # noqa: BLE001
+        return {"numa_node": None, "note": "binding skipped: %r" % (e,)}
 
 
 class ClockSampler:
@@ -126,7 +159,7 @@ def cpu_port_rate(target_seconds: float, max_rows: int):
     n_chunks = int(max(1, min(max_rows // chunk, target_seconds / per_chunk)))
     zs = torch.randn(n_chunks * chunk, E_DIM, generator=g)
     t0 = time.perf_counter()
-    port.quantize_chunked(zs, E, AL, BETA, True, chunk)
+    port.quantize_chunked_timed(zs, E, AL, BETA, True, chunk)
     dt = time.perf_counter() - t0
     rows = n_chunks * chunk
     return rows / dt, torch.get_num_threads(), "%d rows (%d chunks of 65536) of the config-2 workload, train path, %.1f s" % (rows, n_chunks, dt)
@@ -153,11 +186,12 @@ def run_reference(args, rank):
     n_chunks = int(max(1, min(N_PER_GPU // chunk, budget / per_chunk)))
     rows = n_chunks * chunk
     z = torch.randn(rows, E_DIM, generator=g)
+    # quantize_chunked_timed: exactly network/vqvae/quantizer.py:30-67 per chunk + bincount / weighted-mean combine
     for _ in range(args.warmup):
-        port.quantize_chunked(z, E, AL, BETA, True, chunk)
+        port.quantize_chunked_timed(z, E, AL, BETA, True, chunk)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        port.quantize_chunked(z, E, AL, BETA, True, chunk)
+        port.quantize_chunked_timed(z, E, AL, BETA, True, chunk)
     dt = time.perf_counter() - t0
     value = rows * args.steps / dt
     sample = "%d of %d rows per step (%d chunks of 65536), train path" % (rows, N_PER_GPU, n_chunks)
@@ -171,6 +205,104 @@ def run_reference(args, rank):
     }))
 
 
+def run_secondary(torch, tdist, dvq, dev, rank, world, fence):
+    """Driver-timed lines for the other BASELINE configs (whole-job aggregate over `world` GPUs, CUDA events, max over
+    ranks).  Every leg: synthetic inputs resident in HBM, >= 1 warm-up call, 3 timed calls."""
+    import math
+    hbm_gbs, bf16_tf, peak_src, bf16_sus = measured_peaks()
+    out = {"peak_source": peak_src, "bf16_tflops_sustained": bf16_sus}
+
+    def timed(fn, iters=3, warm=1):
+        for _ in range(warm):
+            fn()
+        fence()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        fence()
+        ms = a.elapsed_time(b) / iters
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- config 4 corner: K = 16384, e_dim = 128, 16 777 216 latents in total (rows sharded), train path ----
+    try:
+        K4, D4, N4 = 16384, 128, 16777216 // world
+        g = torch.Generator(device=dev).manual_seed(4000 + rank)
+        cg = torch.Generator(device=dev).manual_seed(4000)
+        vq4 = dvq.VectorQuantizer(K4, D4, BETA, AL).to(dev)
+        vq4.onehot_limit_bytes = 0
+        with torch.no_grad():
+            vq4.embedding.weight.copy_((torch.rand(K4, D4, device=dev, generator=cg) * 2 - 1) / K4)
+        if world > 1:
+            dvq.dist.shard_module(vq4)
+        z4 = torch.randn(N4, D4, device=dev, generator=g)
+
+        def step4():
+            with torch.no_grad():
+                return vq4(z4, True)
+        ms = timed(step4)
+        tf = 2.0 * N4 * world * K4 * D4 / (ms * 1e-3) / 1e12
+        out["config4_k16384_d128"] = {
+            "metric": METRIC, "value": N4 * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "rows_per_gpu": N4, "n_e": K4, "e_dim": D4,
+            "undecided_rows_rank0": vq4.last_counters(N4)[0],
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_sus * world, "unit": "TFLOP/s", "frac": tf / (bf16_sus * world),
+                         "what": "2*N*K*e_dim of the whole call (norm pre-pass + filter + exact refine + finalize) over the sustained BF16 peak x GPUs"}}
+        del z4, vq4
+        torch.cuda.empty_cache()
+    except Exception as e:                                  # noqa: BLE001
+        out["config4_k16384_d128"] = {"error": repr(e)}
+
+    # ---- PointNet encoder: C = 4, P = 3000, 4096 clouds per GPU, default (tcgen05) path ----
+    try:
+        B, P = 4096, 3000
+        torch.manual_seed(0)
+        enc = dvq.PointNetEncoder(channel=4).to(dev).eval().requires_grad_(False)
+        g = torch.Generator(device=dev).manual_seed(3000 + rank)
+        obj = 0.1 * torch.randn(B, 4, P, device=dev, generator=g)
+        obj[:, 3, :] = 0.05 + 0.25 * torch.rand(B, 1, device=dev, generator=g)
+        ms = timed(lambda: enc(obj))
+        flop = B * world * P * 558080.0
+        tf = flop / (ms * 1e-3) / 1e12
+        out["pointnet_c4_p3000"] = {
+            "metric": "pointnet_clouds_per_sec", "value": B * world / (ms * 1e-3), "unit": "clouds/s", "ms_per_call": ms, "clouds_per_gpu": B,
+            "precision": enc.precision,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_sus * world, "unit": "TFLOP/s", "frac": tf / (bf16_sus * world),
+                         "what": "558 080 flop per point (STN trunk + main trunk) over the sustained BF16 peak x GPUs",
+                         "hbm_gbs": B * world * (16.0 * P + 4096) / (ms * 1e-3) / 1e9}}
+        del enc
+    except Exception as e:                                  # noqa: BLE001
+        out["pointnet_c4_p3000"] = {"error": repr(e)}
+        obj = None
+
+    # ---- grasp generation (config 3; at N GPUs the config-5 layout: objects sharded, weights replicated) ----
+    try:
+        from dvq.grasp import pixelcnn_prior
+        from dvq.pixelcnn import GatedPixelCNN
+        torch.manual_seed(0)
+        net = dvq.GraspGenerator().to(dev).eval().requires_grad_(False)
+        torch.manual_seed(1)
+        pcnn = GatedPixelCNN(512, 512, 15).to(dev).eval().requires_grad_(False)
+        pcnn.precision = "tf32"
+        net.prior = pixelcnn_prior(pcnn, n_valid=128)
+        ms = timed(lambda: net.gen(obj))
+        flop = B * world * (2 * P * 558080.0 + 778 * (2 * (3 * 64 + 64 * 128 + 128 * 1024) * 2.0) + 5.8e9)
+        out["grasp_generation_b4096"] = {
+            "metric": "grasps_per_sec", "value": B * world / (ms * 1e-3), "unit": "grasps/s", "ms_per_batch": ms, "batch_per_gpu": B, "points": P,
+            "prior": "GatedPixelCNN(512,512,15), exact row-cached sampler, %s, random init, 128 valid classes" % pcnn.backend_name(),
+            "hand_layer": "linear stub (MANO assets need chumpy: absent)",
+            "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": bf16_sus * world, "unit": "TFLOP/s",
+                         "frac": flop / (ms * 1e-3) / 1e12 / (bf16_sus * world),
+                         "what": "PointNets 3.78 GFLOP + row-cached PixelCNN sampler ~5.8 GFLOP per grasp over the sustained BF16 peak x GPUs"}}
+    except Exception as e:                                  # noqa: BLE001
+        out["grasp_generation_b4096"] = {"error": repr(e)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,6 +312,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 10))")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-3/4/5 lines of the `secondary` dict")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the GPU's NUMA node")
+    ap.add_argument("--raw-nccl", action="store_true", help="all-reduce (hist, sse) through dvq_allreduce_stats instead of torch.distributed")
     ap.add_argument("--e2e-chunk-rows", type=int, default=E2E_CHUNK_ROWS, help="rows per chunk of the host-buffer pipeline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -198,10 +333,13 @@ def main():
     import dvq
     from dvq import _cabi
 
+    numa = {"numa_node": None, "note": "disabled"} if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         tdist.init_process_group("nccl", device_id=dev)
+        if args.raw_nccl:
+            dvq.dist.use_raw_nccl(True)
 
     gen = torch.Generator(device=dev).manual_seed(2000 + rank)
     cb_gen = torch.Generator(device=dev).manual_seed(2000)       # replicated codebook
@@ -277,25 +415,51 @@ def main():
         e2e_s = float(t.item())
     e2e_value = N_PER_GPU * world * e2e_steps / e2e_s
     same_idx = bool(torch.equal(idx_host, idx.cpu()))
+    # copy-only ceiling of the same pipeline: identical chunks, streams and buffers, kernels skipped (DVQ_HOST_COPY_ONLY)
+    zq_scratch = zq_host                                   # (outputs are undefined in this mode: the buffers are reused after the check above)
+    hq.forward(z_host, E_host, True, AL, BETA, out_zq=zq_scratch, out_idx=idx_host, path=vq.path, copy_only=True)
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hq.forward(z_host, E_host, True, AL, BETA, out_zq=zq_scratch, out_idx=idx_host, path=vq.path, copy_only=True)
+    torch.cuda.synchronize(dev)
+    copy_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([copy_s], device=dev, dtype=torch.float64)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        copy_s = float(t.item())
+    copy_value = N_PER_GPU * world * e2e_steps / copy_s
     hq.close()
+    del z_host, zq_host, idx_host, hq
+    secondary = None
+    if not args.no_secondary:
+        del z, out, z_q, enc, idx
+        torch.cuda.empty_cache()
+        secondary = run_secondary(torch, tdist, dvq, dev, rank, world, fence)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        hbm_gbs, bf16_tf, peak_src = measured_peaks()
+        hbm_gbs, bf16_tf, peak_src, bf16_sus = measured_peaks()
         alg_bytes = N_PER_GPU * (8 * E_DIM + 8) + 4 * N_E * E_DIM
         k_ms = prof_ms[1]
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                "traffic": None, "kernel": "vq main kernel (stage 1 of dvq_vq_forward)", "kernel_ms": k_ms,
+                "traffic": None, "traffic_source": None, "kernel": "vq main kernel (stage 1 of dvq_vq_forward)", "kernel_ms": k_ms,
                 "refine_ms": prof_ms[2], "launches_averaged": prof_cnt[1], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "tensor_frac_of_half_bf16_peak": (2.0 * N_PER_GPU * N_E * E_DIM / (k_ms * 1e-3) / 1e12) / (bf16_tf / 2) if bf16_tf else None}
-        tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
-        if os.path.exists(tr):
-            try:
-                roof["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
-            except Exception:
-                pass
+                "whole_step_frac": alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9 / hbm_gbs,
+                # in-step tensor-pipe figure against the SUSTAINED BF16 peak (the kernel is timed inside a long step)
+                "tensor_tflops": 2.0 * N_PER_GPU * N_E * E_DIM / (k_ms * 1e-3) / 1e12,
+                "tensor_frac_of_bf16_sustained": (2.0 * N_PER_GPU * N_E * E_DIM / (k_ms * 1e-3) / 1e12) / bf16_sus if bf16_sus else None}
+        for name in ("traffic_r02.json", "traffic_r01.json"):     # not measured in this run: one `ncu --set full` capture per round
+            tr = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tr):
+                try:
+                    roof["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+                    roof["traffic_source"] = "profiles/%s (ncu --set full capture of this kernel, dram__bytes_read.sum + dram__bytes_write.sum; not re-measured in this run)" % name
+                    break
+                except Exception:
+                    pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, sample = cpu_port_rate(15.0, N_PER_GPU)
@@ -311,7 +475,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_PER_GPU * E_DIM * 4 + N_E * E_DIM * 4,
                     "d2h_bytes_per_step": N_PER_GPU * E_DIM * 4 + N_PER_GPU * 8 + 8, "steps": e2e_steps,
                     "ms_per_step": e2e_s / e2e_steps * 1e3, "api": "dvq_vq_forward_host (pinned host buffers, 3-stream chunk pipeline, %d-row chunks)" % args.e2e_chunk_rows,
-                    "indices_equal_device_path": same_idx},
+                    "indices_equal_device_path": same_idx,
+                    "copy_only_ceiling": {"value": copy_value, "unit": UNIT, "ms_per_step": copy_s / e2e_steps * 1e3,
+                                          "frac_of_ceiling": e2e_value / copy_value,
+                                          "what": "the same chunk pipeline (H2D z, D2H z_q + idx, pinned buffers, 3 streams) with the kernels skipped"},
+                    "numa": numa},
+            "secondary": secondary,
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line))

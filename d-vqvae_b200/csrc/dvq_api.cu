@@ -199,7 +199,11 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
   const bool tc_ok = vq_tc_supported(N, K, D);
   if (path == DVQ_PATH_TC && !tc_ok)
     return fail(DVQ_ERR_BAD_SHAPE, "DVQ_PATH_TC: shape N=%lld K=%d D=%d is not handled by the tcgen05 kernel", (long long)N, K, D);
-  const bool use_tc = tc_ok && path != DVQ_PATH_SIMT;
+  // the tcgen05 kernel moves rows with bulk copies / 128-bit accesses: AUTO falls back to the FP32 kernel for a
+  // (valid) 4-byte-aligned view such as a contiguous tensor with an odd storage offset; an explicit DVQ_PATH_TC
+  // request errors in launch_vq_tc
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(E) | reinterpret_cast<uintptr_t>(z_q)) % 16 == 0;
+  const bool use_tc = tc_ok && path != DVQ_PATH_SIMT && (aligned16 || path == DVQ_PATH_TC);
 
   profile_mark(0, true, s);
   rc = launch_code_norms(E, K, D, ee, s);
@@ -454,7 +458,20 @@ int dvq_host_ctx_create(int64_t chunk_rows, int K_max, int D_max, DvqHostCtx** o
   CTX_CHECK(cudaMalloc(&c->hist_dev, stat_bytes));
   c->sse_dev = reinterpret_cast<double*>(reinterpret_cast<char*>(c->hist_dev) + align_up(sizeof(unsigned long long) * (size_t)K_max, 16));
   c->scal_dev = reinterpret_cast<float*>(c->sse_dev + 1);
-  c->ws_bytes = vq_workspace_layout(chunk_rows, K_max, D_max, 0).total + 4096;
+  // the workspace must serve every shape up to (K_max, D_max): the layout is not monotone in K and D (the tcgen05
+  // path and its buffers exist only for some shapes), so take the maximum over the shape classes
+  size_t ws_need = 0;
+  for (int k = 32; ; k *= 2) {
+    const int kk = k < K_max ? k : K_max;
+    for (int d = 16; ; d *= 2) {
+      const int dd = d < D_max ? d : D_max;
+      const size_t t = vq_workspace_layout(chunk_rows, kk, dd, 0).total;
+      ws_need = t > ws_need ? t : ws_need;
+      if (dd == D_max) break;
+    }
+    if (kk == K_max) break;
+  }
+  c->ws_bytes = ws_need + 4096;
   CTX_CHECK(cudaMalloc(&c->ws, c->ws_bytes));
 #undef CTX_CHECK
   *out = c;
@@ -495,9 +512,11 @@ int dvq_vq_forward_host(DvqHostCtx* c, const float* z_host, const float* E_host,
     DVQ_CUDA_CHECK(cudaMemcpyAsync(c->z_dev[b], z_host + r0 * D, row_bytes * rows, cudaMemcpyHostToDevice, c->s_in));
     DVQ_CUDA_CHECK(cudaEventRecord(c->ev_in[b], c->s_in));
     DVQ_CUDA_CHECK(cudaStreamWaitEvent(c->s_run, c->ev_in[b], 0));
-    rc = dvq_vq_forward(c->z_dev[b], c->E_dev, rows, K, D, flags, c->zq_dev[b], c->idx_dev[b], nullptr, c->hist_dev,
-                        c->sse_dev, c->ws, c->ws_bytes, c->s_run);
-    if (rc) return rc;
+    if (!(flags & DVQ_HOST_COPY_ONLY)) {
+      rc = dvq_vq_forward(c->z_dev[b], c->E_dev, rows, K, D, flags, c->zq_dev[b], c->idx_dev[b], nullptr, c->hist_dev,
+                          c->sse_dev, c->ws, c->ws_bytes, c->s_run);
+      if (rc) return rc;
+    }
     DVQ_CUDA_CHECK(cudaEventRecord(c->ev_run[b], c->s_run));
     DVQ_CUDA_CHECK(cudaStreamWaitEvent(c->s_out, c->ev_run[b], 0));
     DVQ_CUDA_CHECK(cudaMemcpyAsync(zq_host + r0 * D, c->zq_dev[b], row_bytes * rows, cudaMemcpyDeviceToHost, c->s_out));
@@ -505,7 +524,7 @@ int dvq_vq_forward_host(DvqHostCtx* c, const float* z_host, const float* E_host,
     DVQ_CUDA_CHECK(cudaEventRecord(c->ev_out[b], c->s_out));
   }
   float scal[2] = {0.f, 0.f};
-  if (train && N > 0) {
+  if (train && N > 0 && !(flags & DVQ_HOST_COPY_ONLY)) {
     rc = launch_finalize(c->hist_dev, c->sse_dev, N, K, D, al, beta, c->scal_dev, c->scal_dev + 1, c->s_run);
     if (rc) return rc;
     DVQ_CUDA_CHECK(cudaMemcpyAsync(scal, c->scal_dev, sizeof(scal), cudaMemcpyDeviceToHost, c->s_run));

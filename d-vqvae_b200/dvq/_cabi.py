@@ -20,6 +20,7 @@ DVQ_WRITE_ONEHOT = 0x2
 DVQ_PATH_AUTO = 0x00
 DVQ_PATH_SIMT = 0x10
 DVQ_PATH_TC = 0x20
+DVQ_HOST_COPY_ONLY = 0x100
 
 STATUS_NAMES = {0: "DVQ_OK", -1: "DVQ_ERR_BAD_SHAPE", -2: "DVQ_ERR_BAD_ALIGN", -3: "DVQ_ERR_UNSUPPORTED_ARCH",
                 -4: "DVQ_ERR_WORKSPACE", -5: "DVQ_ERR_CUDA", -6: "DVQ_ERR_NCCL", -7: "DVQ_ERR_BAD_ARG"}

@@ -5,9 +5,12 @@ The integer histogram makes perplexity independent of the number of ranks exactl
 differs only by fp64 summation order.  The inference path and PointNet need no collective.
 
 One process per GPU, launched by torchrun; ``torch.distributed`` provides rendezvous and the
-communicator.  On CUDA tensors with the NCCL backend the reduction goes through the C ABI
-(``dvq_allreduce_stats``: both buffers in one NCCL group on the current stream, using torch's
-own ``ncclComm_t``); any other backend (gloo in the CPU tests) uses ``all_reduce`` directly.
+communicator.  By default the reduction is two ``torch.distributed.all_reduce`` calls on views of the
+packed stats tensor (hist as int64, sse as float64) — inside ProcessGroupNCCL's own sequencing, watchdog
+and flight recorder.  ``use_raw_nccl(True)`` opts into the C-ABI hook instead (``dvq_allreduce_stats``:
+both buffers in ONE NCCL group enqueued on the caller's current stream with torch's ``ncclComm_t``, no
+stream hop — ~20 us less per step, but outside torch's bookkeeping and dependent on the private
+``_comm_ptr()`` accessor).
 """
 from __future__ import annotations
 
@@ -20,6 +23,15 @@ def shard_bounds(n_rows: int, rank: int, world: int):
     base, rem = divmod(int(n_rows), int(world))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+_RAW_NCCL = False
+
+
+def use_raw_nccl(on: bool = True) -> None:
+    """Opt in to / out of the raw-NCCL hook (see the module docstring)."""
+    global _RAW_NCCL
+    _RAW_NCCL = bool(on)
 
 
 def _nccl_comm_ptr(group, device):
@@ -43,7 +55,7 @@ def allreduce_stats(stats: torch.Tensor, n_e: int, n_local: int, group=None) -> 
     hist = stats[:n_e]
     sse = stats[n_e:n_e + 1].view(torch.float64)
     done = False
-    if stats.is_cuda and tdist.get_backend(group) == "nccl":
+    if _RAW_NCCL and stats.is_cuda and tdist.get_backend(group) == "nccl":
         comm = _nccl_comm_ptr(group, stats.device)
         if comm is not None:
             from . import _cabi

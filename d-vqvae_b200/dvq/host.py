@@ -34,7 +34,7 @@ class HostQuantizer:
             pass
 
     def forward(self, z: torch.Tensor, codebook: torch.Tensor, istrain: bool, al: float = 1.0, beta: float = 0.25,
-                out_zq: torch.Tensor | None = None, out_idx: torch.Tensor | None = None, path: int = 0):
+                out_zq: torch.Tensor | None = None, out_idx: torch.Tensor | None = None, path: int = 0, copy_only: bool = False):
         """z [.., D] and codebook [K, D]: fp32 CPU tensors (pin them for full copy/compute overlap).
         Returns (loss, z_q, perplexity, idx[N,1]) if ``istrain`` else (idx[N,1], z_q) — host tensors."""
         if z.is_cuda or codebook.is_cuda:
@@ -48,7 +48,7 @@ class HostQuantizer:
         zq = out_zq if out_zq is not None else torch.empty(z.shape, dtype=torch.float32, pin_memory=True)
         idx = out_idx if out_idx is not None else torch.empty((n, 1), dtype=torch.int64, pin_memory=True)
         loss, ppl = C.c_float(), C.c_float()
-        flags = (_cabi.DVQ_TRAIN if istrain else 0) | path
+        flags = (_cabi.DVQ_TRAIN if istrain else 0) | path | (_cabi.DVQ_HOST_COPY_ONLY if copy_only else 0)   # copy_only: the pipeline's copies without kernels (bench ceiling; outputs undefined)
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib.dvq_vq_forward_host(
                 self._ctx, z.data_ptr(), codebook.data_ptr(), n, k, d, flags, float(al), float(beta),

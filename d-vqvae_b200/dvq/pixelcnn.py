@@ -78,6 +78,10 @@ def _weights_init(m):                                        # models.py:9-16
             pass
 
 
+def _invalidate_after_load(module, incompatible_keys):
+    module.invalidate()
+
+
 class GatedPixelCNN(nn.Module):
     def __init__(self, input_dim=256, dim=128, n_layers=15, n_classes=128):
         super().__init__()
@@ -91,6 +95,7 @@ class GatedPixelCNN(nn.Module):
         self.apply(_weights_init)
         self.precision = "fp32"       # "fp32" | "tf32": the sampler's GEMMs (the reference's cuDNN convs are TF32 by default on GPU)
         self._packed = None
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
 
     # ---- the reference forward, unchanged semantics (models.py:159-173) ---------------------------------
     def forward(self, x, label):
@@ -102,11 +107,29 @@ class GatedPixelCNN(nn.Module):
         return self.output_conv(x_h)
 
     # ---- packed weights for the cached sampler ----------------------------------------------------------
+    repack_every_call = False
+
+    def invalidate(self):
+        """Drop the packed weights.  The cache key is (data_ptr, _version) of every parameter: optimizer steps,
+        ``copy_`` and ``.to()`` are seen; in-place edits through ``.data`` (the reference's ``weights_init`` /
+        ``make_causal`` style) do not bump ``_version`` — call ``invalidate()`` after such an edit (a
+        ``load_state_dict`` does it by itself), or set ``repack_every_call = True``."""
+        self._packed = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_packed"] = None
+        return d
+
     def _pack(self):
         """[taps*dim, 2*dim] matrices, masks applied (as make_causal leaves the weights after the first
         reference forward).  Re-packed whenever a parameter version changes."""
-        key = tuple(p._version for p in self.parameters()) + (next(self.parameters()).device,)
-        if self._packed is not None and self._packed[0] == key:
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (str(next(self.parameters()).device),)
+        if self._packed is not None and self._packed[0] == key and not self.repack_every_call:
             return self._packed[1]
         packs = []
         for layer in self.layers:
@@ -132,6 +155,10 @@ class GatedPixelCNN(nn.Module):
                     w2=self.output_conv[2].weight.detach()[:, :, 0, 0].t().contiguous(), b2=self.output_conv[2].bias.detach())
         self._packed = (key, (packs, head))
         return self._packed[1]
+
+    def backend_name(self):
+        """What executes the sampler's contractions (for benchmark records)."""
+        return {"fp32": "FP32 cuBLAS GEMMs", "tf32": "TF32 cuBLAS GEMMs"}.get(self.precision, self.precision)
 
     def _matmul_ctx(self):
         if self.precision == "tf32" and torch.cuda.is_available():

@@ -53,6 +53,10 @@ def _fold(lin_w, lin_b, bn):
     return (w * s[:, None]).float().contiguous(), ((b - bn.running_mean.detach().double()) * s + bn.bias.detach().double()).float().contiguous()
 
 
+def _invalidate_after_load(module, incompatible_keys):
+    module.invalidate()
+
+
 class PointNetEncoder(nn.Module):
     def __init__(self, global_feat=True, feature_transform=False, channel=3):
         super().__init__()
@@ -72,21 +76,49 @@ class PointNetEncoder(nn.Module):
         self.global_feat = global_feat
         self.feature_transform = feature_transform
         self.channel = channel
-        # "fp32": all-FP32 CUDA-core kernel (parity 5e-5 vs the CPU reference); "fp16_tc": layers 2-3 on
-        # tcgen05 tensor cores, FP16 operands / FP32 accumulation (3e-3; what TF32 cuDNN gives the reference)
-        self.precision = "fp32"
+        # "fp16_tc" (default): layers 2-3 on tcgen05 tensor cores, FP16 operands / FP32 accumulation — the same 10-bit
+        # operand mantissa as the TF32 cuDNN convolutions the reference runs on a GPU (torch.backends.cudnn.allow_tf32
+        # is True by default), parity 1e-3 of the feature scale; "fp32": all-FP32 CUDA-core kernel (parity 5e-5 vs the
+        # CPU reference, 14x slower)
+        self.precision = "fp16_tc"
         self._folded = None
         self._folded_key = None
         self._ws = None
+        # a checkpoint load replaces parameter contents without necessarily bumping every version counter
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
 
     # -------------------------------------------------------------- BN fold cache
+    def invalidate(self):
+        """Drop the cached BN-folded weights.  The cache is keyed on (data_ptr, _version, device) of every
+        parameter and buffer, which catches optimizer steps, ``copy_``, ``load_state_dict`` and ``.to()``, but NOT
+        in-place edits through ``.data`` (``w.data.mul_()``, ``running_mean.data.fill_()`` do not bump ``_version``):
+        after such an edit call ``invalidate()``, or set ``refold_every_call = True``."""
+        self._folded = None
+        self._folded_key = None
+
+    refold_every_call = False
+    _warned_detached = False
+
+    def _apply(self, fn, *args, **kwargs):     # .to() / .cuda() / .float(): new storage
+        self.invalidate()
+        self._ws = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def __getstate__(self):                    # deepcopy / pickle / torch.save(module): caches hold raw device pointers
+        d = self.__dict__.copy()
+        d["_folded"] = None
+        d["_folded_key"] = None
+        d["_ws"] = None
+        return d
+
     def _fold_key(self):
         return tuple((t.data_ptr(), t._version, str(t.device)) for t in list(self.parameters()) + list(self.buffers()))
 
     def folded_weights(self):
         key = self._fold_key()
-        if self._folded is not None and key == self._folded_key:
-            return self._folded
+        if self._folded is not None and key == self._folded_key and not self.refold_every_call:
+            blob, offs = self._folded
+            return blob, self._weights_struct(blob, offs)
         s = self.stn
         parts = [
             _fold(s.conv1.weight, s.conv1.bias, s.bn1), _fold(s.conv2.weight, s.conv2.bias, s.bn2),
@@ -104,12 +136,16 @@ class PointNetEncoder(nn.Module):
         blob = torch.zeros(total, dtype=torch.float32, device=flat[0].device)
         for t, o in zip(flat, offs):
             blob[o:o + t.numel()] = t.reshape(-1)
+        self._folded = (blob, tuple(offs))     # (only tensors and ints are cached: the module stays picklable)
+        self._folded_key = key
+        return blob, self._weights_struct(blob, offs)
+
+    @staticmethod
+    def _weights_struct(blob, offs):
         st = _cabi.PointNetWeights()
         for (name, _), o in zip(_cabi.PointNetWeights._fields_, offs):
             setattr(st, name, blob.data_ptr() + 4 * o)
-        self._folded = (blob, st)
-        self._folded_key = key
-        return self._folded
+        return st
 
     def forward(self, x):
         if self.training:
@@ -121,6 +157,18 @@ class PointNetEncoder(nn.Module):
             raise ValueError("x must be [B, %d, P]; got %s" % (self.channel, tuple(x.shape)))
         if not x.is_cuda or not self.conv1.weight.is_cuda:
             raise ValueError("dvq.PointNetEncoder has no CPU path: x and the weights must be CUDA tensors")
+        if torch.is_grad_enabled():
+            # the fused kernel has no backward.  An input that asks for gradients is an error; parameters that merely
+            # still have requires_grad=True (the reference scripts call GenNet.gen without torch.no_grad():
+            # gen_diverse_grasp_obman.py:236) get detached outputs and a one-time warning
+            if x.requires_grad:
+                raise RuntimeError("dvq.PointNetEncoder is inference-only (no autograd through the fused kernel): "
+                                   "detach x or call the encoder under torch.no_grad()")
+            if not PointNetEncoder._warned_detached and any(p.requires_grad for p in self.parameters()):
+                PointNetEncoder._warned_detached = True
+                import warnings
+                warnings.warn("dvq.PointNetEncoder returns detached features: its parameters will receive no gradient "
+                              "(inference-only fused kernel); use the reference encoder for training / fine-tuning")
         x = x.detach()
         if not x.is_contiguous():
             x = x.contiguous()   # e.g. the permute at gen_net.py:120

@@ -65,17 +65,25 @@ class _VQFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, weight, module):
         loss, z_q, ppl, idx = module._forward_train_raw(z, weight)
-        ctx.save_for_backward(z, weight, idx)
+        # rows the returned loss is a mean over: the local count, or — row-sharded — the all-reduced histogram total
+        # (a device scalar: no host sync).  The gradients below are the exact partial derivatives of the RETURNED
+        # (global) loss with respect to the local rows of z and the local rows' contribution to dE; summing dE over
+        # the ranks (all-reduce SUM) gives the exact codebook gradient.
+        if module.process_group is not None:
+            n_rows = module.last_stats[:module.n_e].sum().to(torch.float32)
+        else:
+            n_rows = torch.tensor(float(z.numel() // weight.shape[1]), device=z.device)
+        ctx.save_for_backward(z, weight, idx, n_rows)
         ctx.al, ctx.beta = float(module.al), float(module.beta)
         ctx.mark_non_differentiable(ppl, idx)
         return loss, z_q, ppl, idx
 
     @staticmethod
     def backward(ctx, g_loss, g_zq, _g_ppl, _g_idx):
-        z, weight, idx = ctx.saved_tensors
+        z, weight, idx, n_rows = ctx.saved_tensors
         flat = z.reshape(-1, weight.shape[1])
         e = weight.index_select(0, idx.view(-1))
-        scale = 2.0 / flat.numel()
+        scale = 2.0 / (n_rows * weight.shape[1])
         diff = (flat - e) * scale
         gz = gw = None
         if ctx.needs_input_grad[0]:
@@ -93,6 +101,13 @@ class VectorQuantizer(nn.Module):
     """Discretisation bottleneck of the VQ-VAE (reference: network/vqvae/quantizer.py:10)."""
 
     onehot_limit_bytes = 2 << 30
+
+    def __getstate__(self):     # deepcopy / pickle: the workspace is a cache, a process group cannot be pickled
+        d = self.__dict__.copy()
+        d["_ws"] = None
+        d["process_group"] = None
+        d.pop("last_stats", None)
+        return d
 
     def __init__(self, n_e, e_dim, beta, al):
         super().__init__()
@@ -117,8 +132,6 @@ class VectorQuantizer(nn.Module):
                              "(got z on %s, codebook on %s)" % (z.device, weight.device))
         if z.device != weight.device:
             raise ValueError("z (%s) and the codebook (%s) are on different devices" % (z.device, weight.device))
-        if not z.is_contiguous():
-            raise ValueError("z must be contiguous (the reference's .view(-1, e_dim) has the same requirement)")
         if z.numel() % self.e_dim != 0:
             raise RuntimeError("shape '[-1, %d]' is invalid for input of size %d" % (self.e_dim, z.numel()))
         if weight.dtype != torch.float32 or not weight.is_contiguous() or tuple(weight.shape) != (self.n_e, self.e_dim):
@@ -162,7 +175,8 @@ class VectorQuantizer(nn.Module):
         idx = torch.empty((n, 1), dtype=torch.int64, device=dev)
         # stats = hist[K] (uint64) | sse (float64), one buffer so the all-reduce is one message
         stats = torch.zeros(self.n_e + 1, dtype=torch.int64, device=dev)
-        self._launch(z, weight, _cabi.DVQ_TRAIN | self.path, z_q, idx, None, stats)
+        if n > 0:   # (a rank with an empty shard still joins the collective below with zeroed stats)
+            self._launch(z, weight, _cabi.DVQ_TRAIN | self.path, z_q, idx, None, stats)
         n_total = n
         if self.process_group is not None:
             n_total = _dist.allreduce_stats(stats, self.n_e, n, self.process_group)
@@ -179,6 +193,10 @@ class VectorQuantizer(nn.Module):
     def forward(self, z, istrain):
         weight = self.embedding.weight
         self._check(z, weight)
+        if not z.is_contiguous():
+            # the reference's .view(-1, e_dim) accepts stride-compatible slices (e.g. h[:, :256]) and raises for the
+            # rest; the kernels read dense rows, so any layout is copied once (autograd flows through the copy)
+            z = z.contiguous()
         n = z.numel() // self.e_dim
         if not istrain:
             # quantizer.py:44-54
@@ -189,7 +207,7 @@ class VectorQuantizer(nn.Module):
             return idx, z_q
 
         # quantizer.py:35-43, 56-67
-        if n == 0:  # torch.mean over an empty tensor is NaN in the reference as well
+        if n == 0 and self.process_group is None:  # torch.mean over an empty tensor is NaN in the reference as well
             nan = torch.full((), float("nan"), device=z.device)
             return nan, torch.empty_like(z), nan.clone(), torch.empty((0, self.n_e), device=z.device), \
                 torch.empty((0, 1), dtype=torch.int64, device=z.device)

@@ -53,6 +53,8 @@ typedef enum DvqStatus {
 #define DVQ_PATH_SIMT 0x10    /* force the all-FP32 CUDA-core kernel                            */
 #define DVQ_PATH_TC 0x20      /* force the tcgen05 kernel (error if the shape is unsupported)   */
 #define DVQ_PATH_MASK 0x30
+#define DVQ_HOST_COPY_ONLY 0x100 /* dvq_vq_forward_host only: run the chunk pipeline's H2D / D2H copies without the
+                                    kernels (outputs are undefined) - the copy-only ceiling of the host-buffer path */
 
 DVQ_API int dvq_abi_version(void);
 DVQ_API const char* dvq_last_error(void);

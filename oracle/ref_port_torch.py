@@ -41,6 +41,36 @@ def quantize_rows(z: torch.Tensor, codebook: torch.Tensor, al: float, beta: floa
 
 
 @torch.no_grad()
+def quantize_chunked_timed(z: torch.Tensor, codebook: torch.Tensor, al: float, beta: float, train: bool, chunk: int = 65536):
+    """The timed form for bench.py: per 65 536-row chunk EXACTLY the reference forward (quantize_rows), and the
+    cheapest possible combination of the scalar outputs — row-weighted mean of the chunk losses and an integer
+    ``bincount`` of the chunk's indices for the perplexity.  No fp64 side computation is timed (round 1's
+    ``quantize_chunked`` re-derived the histogram and the SSE in fp64, +36-44 % per chunk)."""
+    n_e, e_dim = codebook.shape
+    flat = z.view(-1, e_dim)
+    n = flat.shape[0]
+    idx = torch.empty(n, 1, dtype=torch.int64)
+    z_q = torch.empty_like(flat)
+    hist = torch.zeros(n_e, dtype=torch.int64)
+    loss_rows = 0.0
+    for s in range(0, n, chunk):
+        zc = flat[s:s + chunk]
+        if train:
+            lc, qc, _, _, ic = quantize_rows(zc, codebook, al, beta, True)
+            hist += torch.bincount(ic.view(-1), minlength=n_e)
+            loss_rows += float(lc) * zc.shape[0]
+        else:
+            ic, qc = quantize_rows(zc, codebook, al, beta, False)
+        idx[s:s + chunk] = ic
+        z_q[s:s + chunk] = qc
+    if not train:
+        return idx, z_q.view(z.shape)
+    p = hist.double() / n
+    perplexity = torch.exp(-torch.sum(p * torch.log(p + 1e-10))).float()
+    return torch.tensor(loss_rows / n, dtype=torch.float32), z_q.view(z.shape), perplexity, None, idx
+
+
+@torch.no_grad()
 def quantize_chunked(z: torch.Tensor, codebook: torch.Tensor, al: float, beta: float,
                      train: bool, chunk: int = 65536):
     """The reference cannot hold N x K at BASELINE config 2/4 sizes; per-row

@@ -133,3 +133,35 @@ def test_tc_shared_memory_plan_per_shape():
     assert plan(16384, 256)["a_bufs"] == 1 and plan(16384, 512)["ds"] == 32
     # shapes the tensor-core path does not take
     assert plan(500, 64)["ok"] == 0 and plan(512, 48)["ok"] == 0 and plan(32768, 64)["ok"] == 0
+
+
+def test_module_caches_survive_deepcopy_and_see_reloaded_weights():
+    """cached device-pointer structs made the modules unpicklable, and the fold / pack caches could go
+    stale.  CPU-only checks of the host logic: deepcopy / pickle work, load_state_dict invalidates the caches."""
+    import copy
+    import pickle
+
+    import torch
+    import dvq
+    from dvq.pixelcnn import GatedPixelCNN
+    enc = dvq.PointNetEncoder(channel=4).eval()
+    enc._folded = (torch.zeros(4), (0,))
+    enc._folded_key = ("stale",)
+    enc2 = copy.deepcopy(enc)
+    assert enc2._folded is None and enc2._ws is None
+    pickle.loads(pickle.dumps(enc))
+    enc.load_state_dict(enc.state_dict())
+    assert enc._folded is None                                # the post-hook dropped the cache
+    enc._folded = (torch.zeros(4), (0,))
+    enc.invalidate()
+    assert enc._folded is None and enc.precision == "fp16_tc"
+    vq = dvq.VectorQuantizer(16, 8, 0.25, 1.0)
+    vq.process_group = object()
+    vq2 = copy.deepcopy(vq)
+    assert vq2.process_group is None and torch.equal(vq2.embedding.weight, vq.embedding.weight)
+    pc = GatedPixelCNN(8, 8, 2, n_classes=4)
+    packs, head = pc._pack()
+    assert pc._packed is not None
+    pc.load_state_dict(pc.state_dict())
+    assert pc._packed is None
+    copy.deepcopy(pc)

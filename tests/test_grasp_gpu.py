@@ -14,6 +14,8 @@ def test_grasp_pipeline_matches_oracle_stages():
     import dvq
     torch.manual_seed(0)
     net = dvq.GraspGenerator().cuda().eval()
+    for m in (net.obj_encoder_type, net.obj_encoder_pos, net.recon_encoder):
+        m.precision = "fp32"                                  # stage-by-stage FP32 oracle bars below
     for name in ("obj_encoder_type", "obj_encoder_pos"):
         getattr(net, name).load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in po.make_state(hash(name) % 1000, 4).items()})
     net.recon_encoder.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in po.make_state(77, 3).items()})

@@ -13,11 +13,14 @@ pytestmark = pytest.mark.gpu
 TOL = 5e-5
 
 
-def _encoder(seed, c):
+def _encoder(seed, c, precision="fp32"):
+    """The FP32 CUDA-core kernel unless a test asks for the default (tcgen05, "fp16_tc")."""
     import dvq
     net = dvq.PointNetEncoder(global_feat=True, feature_transform=False, channel=c)
+    assert net.precision == "fp16_tc"                        # the drop-in default is the tensor-core path
+    net.precision = precision
     net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in po.make_state(seed, c).items()}, strict=True)
-    return net.cuda().eval()
+    return net.cuda().eval().requires_grad_(False)
 
 
 @pytest.mark.parametrize("name", PN_CASES)
@@ -64,7 +67,7 @@ def test_pointnet_vs_oracle_larger_batch():
 
 def test_pointnet_refuses_training_mode_and_bad_shapes():
     import dvq
-    net = dvq.PointNetEncoder(channel=4).cuda()
+    net = dvq.PointNetEncoder(channel=4).cuda().requires_grad_(False)
     with pytest.raises(RuntimeError, match="eval"):
         net(torch.randn(1, 4, 8, device="cuda"))
     net.eval()
@@ -78,9 +81,16 @@ def test_pointnet_refuses_training_mode_and_bad_shapes():
         net.conv3.weight.mul_(2.0)
     f1, _, _ = net(torch.ones(1, 4, 5, device="cuda"))
     assert not torch.equal(f0, f1)
+    # an edit through .data does not bump the version counter: invalidate() is the documented way
+    net.conv3.weight.data.mul_(0.5)
+    net.invalidate()
+    f2, _, _ = net(torch.ones(1, 4, 5, device="cuda"))
+    assert torch.allclose(f2, f0, rtol=1e-3, atol=1e-5)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        net(torch.ones(1, 4, 5, device="cuda", requires_grad=True))
 
 
-TOL_TC = 3e-3   # FP16 operands (10-bit mantissa, = the TF32 cuDNN path of the reference on a GPU), FP32 accumulation
+TOL_TC = 1e-3   # FP16 operands (10-bit mantissa, = the TF32 cuDNN path of the reference on a GPU), FP32 accumulation; measured 2.6e-4
 
 
 @pytest.mark.parametrize("name", PN_CASES)

@@ -4,6 +4,7 @@ reference.  Bars: indices identical outside the FP64 near-tie band (rel gap < 1e
 given the index, loss / perplexity within 1e-5 relative."""
 import ctypes
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -130,6 +131,16 @@ def test_config2_full_size_properties(variant, pname, path):
     assert rel_err(loss.item(), np.float32(np.float32(1.0) * np.float32(mse) + np.float32(0.25) * np.float32(mse))) < REL
     p = hist.double() / N
     assert rel_err(ppl.item(), torch.exp(-(p * torch.log(p + 1e-10)).sum()).item()) < REL
+    # every row against the all-FP32 kernel of the same library (band rule on the rows that differ)
+    from dvq import _cabi
+    if path != _cabi.DVQ_PATH_SIMT:
+        ms = _module(E.cpu().numpy(), 1.0, 0.25, _cabi.DVQ_PATH_SIMT)
+        with torch.no_grad():
+            idx_s, zq_s = ms(z, False)
+        _assert_rows_within_band(z, E, flat, idx_s.view(-1))
+        same = flat == idx_s.view(-1)
+        assert torch.equal(zq_i[same], zq_s[same])
+        del idx_s, zq_s
     # idempotence: quantising z_q returns the same codes with zero error
     idx2, zq2 = m(zq_i, False)
     d_self = vo.allowed_index_mismatch(zq_i[:65536].cpu().numpy(), E.cpu().numpy(), idx2[:65536].cpu().numpy(), idx[:65536].cpu().numpy())
@@ -140,6 +151,76 @@ def test_config2_full_size_properties(variant, pname, path):
     ridx, _ = vo.forward_infer(zs, E.cpu().numpy())
     n_mis, n_bad, worst = vo.allowed_index_mismatch(zs, E.cpu().numpy(), flat[rows].cpu().numpy(), ridx)
     assert n_bad == 0, (n_mis, worst)
+
+
+def _assert_rows_within_band(z, E, idx_a, idx_b, max_rows=200000):
+    """All rows compared on the GPU; the (few) rows whose indices differ are copied to the host and must satisfy
+    the FP64 near-tie rule (oracle.allowed_index_mismatch)."""
+    rows = (idx_a != idx_b).nonzero().view(-1)
+    assert rows.numel() <= max_rows, rows.numel()
+    if rows.numel() == 0:
+        return 0
+    zs = z[rows].cpu().numpy()
+    n_mis, n_bad, worst = vo.allowed_index_mismatch(zs, E.cpu().numpy(), idx_a[rows].cpu().numpy(), idx_b[rows].cpu().numpy())
+    assert n_bad == 0, (n_mis, worst)
+    return n_mis
+
+
+@pytest.mark.parametrize("N,K,D", [(16777216, 16384, 64), (4194304, 4096, 256)])
+def test_config4_corners_full_size_all_rows(N, K, D):
+    """Two corners of BASELINE config 4 at full per-GPU size (16.8M rows on one GPU; the 4-GPU shard of the
+    e_dim 256 shape): every row of the tcgen05 path against the all-FP32 kernel (band rule on differing rows),
+    z_q / histogram / loss consistency on all rows."""
+    from dvq import _cabi
+    gen = torch.Generator(device="cuda").manual_seed(4000 + K + D)
+    E = (torch.rand(K, D, device="cuda", generator=gen) * 2 - 1) / K
+    z = torch.randn(N, D, device="cuda", generator=gen)
+    mt = _module(E.cpu().numpy(), 1.0, 0.25, _cabi.DVQ_PATH_TC)
+    mt.onehot_limit_bytes = 0
+    with torch.no_grad():
+        loss, zq, ppl, _, idx = mt(z, True)
+    assert mt.last_counters(N)[1] == 0
+    flat = idx.view(-1)
+    hist = torch.bincount(flat, minlength=K)
+    assert int(hist.sum()) == N and torch.equal(mt.last_stats[:K], hist)
+    CH = 1 << 21
+    sse = 0.0
+    for s0 in range(0, N, CH):                                   # chunked: no second N x D temporary
+        e = E[flat[s0:s0 + CH]]
+        zc = z[s0:s0 + CH]
+        assert torch.equal(zq[s0:s0 + CH], zc + (e - zc))
+        sse += float(((e - zc).double() ** 2).sum())
+    mse = sse / (N * D)
+    assert rel_err(loss.item(), np.float32(np.float32(mse) + np.float32(0.25) * np.float32(mse))) < REL
+    del zq
+    ms = _module(E.cpu().numpy(), 1.0, 0.25, _cabi.DVQ_PATH_SIMT)
+    with torch.no_grad():
+        idx_s, zq_s = ms(z, False)
+    del zq_s
+    _assert_rows_within_band(z, E, flat, idx_s.view(-1), max_rows=N // 50)
+
+
+@pytest.mark.parametrize("name", ["vq_ragged", "vq_3d_view", "vq_k512_d64"])
+@pytest.mark.parametrize("pname,path", _paths() if torch.cuda.is_available() else [("simt", 0x10)])
+def test_backward_matches_reference_autograd(name, pname, path):
+    """Gradients through dvq.VectorQuantizer == gradients of the REAL reference's autograd graph
+    (tests/golden/vq_grads_*.npz, made by oracle/gen_golden_grads.py from network/vqvae/quantizer.py:36-60)."""
+    import hashlib
+    z, E, al, beta = vq_inputs(name)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vq_grads_%s.npz" % name))
+    seed = int(hashlib.sha256(("grad" + name).encode()).hexdigest()[:6], 16)
+    w = torch.from_numpy(np.random.RandomState(seed).standard_normal(z.shape).astype(np.float32)).cuda()
+    m = _module(E, al, beta, path)
+    zt = torch.from_numpy(z).cuda().requires_grad_(True)
+    loss, zq, ppl, enc, idx = m(zt, True)
+    obj = 3.0 * loss + (zq * zq).sum() + 0.5 * (zq * w).sum()
+    obj.backward()
+    assert rel_err(obj.item(), g["obj"]) < 1e-5
+    same = (idx.cpu().numpy().reshape(-1) == g["idx"].reshape(-1))
+    dz = zt.grad.cpu().numpy().reshape(-1, E.shape[1])
+    assert np.allclose(dz[same], g["dz"].reshape(-1, E.shape[1])[same], rtol=1e-5, atol=1e-7)
+    if same.all():
+        assert np.allclose(m.embedding.weight.grad.cpu().numpy(), g["dE"], rtol=1e-5, atol=1e-8)
 
 
 def test_get_emb_and_wrapper_api():
@@ -188,8 +269,17 @@ def test_input_validation_and_abi_errors():
         m(torch.randn(4, 8, device="cuda").half(), True)
     with pytest.raises(RuntimeError, match="invalid for input of size"):
         m(torch.randn(3, 7, device="cuda"), True)
-    with pytest.raises(ValueError, match="contiguous"):
-        m(torch.randn(8, 4, device="cuda").t(), True)
+    # non-contiguous z (e.g. a slice h[:, :8] of a wider activation, which the reference's .view accepts): copied once
+    wide = torch.randn(6, 24, device="cuda")
+    i_s, q_s = m(wide[:, :8], False)
+    i_c, q_c = m(wide[:, :8].contiguous(), False)
+    assert torch.equal(i_s, i_c) and torch.equal(q_s, q_c)
+    # an odd storage offset (4-byte aligned only): AUTO takes the FP32 kernel instead of failing the tcgen05 alignment check
+    m64 = dvq.VectorQuantizer(64, 64, 0.25, 1).cuda()
+    buf = torch.randn(300 * 64 + 1, device="cuda")
+    i_o, q_o = m64(buf[1:].view(300, 64), False)
+    i_a, q_a = m64(buf[1:].view(300, 64).clone(), False)
+    assert torch.equal(i_o, i_a) and torch.equal(q_o, q_a)
     l, q, p, e, i = m(torch.empty(0, 8, device="cuda"), True)
     assert tuple(q.shape) == (0, 8) and tuple(i.shape) == (0, 1)
     i0, q0 = m(torch.empty(0, 8, device="cuda"), False)
@@ -232,8 +322,13 @@ def test_host_buffer_entry_equals_device_entry(train):
     hq.close()
 
 
-@pytest.mark.parametrize("K,D", [(800, 64), (4096, 64), (1536, 32), (16384, 64),
-                                 (512, 128), (128, 256), (2048, 128), (4096, 256), (992, 128), (1024, 256), (512, 512), (2048, 512)])
+# every (K, e_dim) pair of BASELINE config 4 — the streamed kernel picks a shared-memory plan per shape
+# (smem_layout in vq_tc_sm100.cu), so each pair is its own code path — plus ragged / real-model shapes
+CONFIG4_SHAPES = [(K, D) for K in (512, 1024, 2048, 4096, 8192, 16384) for D in (64, 128, 256, 512)]
+EXTRA_SHAPES = [(800, 64), (1536, 32), (128, 256), (992, 128), (960, 256), (32, 16), (256, 32)]
+
+
+@pytest.mark.parametrize("K,D", CONFIG4_SHAPES + EXTRA_SHAPES)
 @pytest.mark.parametrize("variant", ["default", "variant_b"])
 def test_streamed_codebook_tc_path(K, D, variant):
     """Codebooks larger than the shared-memory-resident limit are streamed block by block through the
@@ -241,7 +336,7 @@ def test_streamed_codebook_tc_path(K, D, variant):
     model's K = 128, D = 256 codebooks), K > 992 records candidates as sub-chunk lists: parity against the
     all-FP32 kernel and the oracle (band rule), ragged N."""
     from dvq import _cabi
-    N = 20000 + 37
+    N = (20000 if K * D <= 2048 * 512 else 6000) + 37        # (bounds the CPU oracle's N x K x e_dim product)
     if variant == "default":
         E = vo.default_codebook(K, D, 31)
         z = vo.normal_latents(N, D, 32)
