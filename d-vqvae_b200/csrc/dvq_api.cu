@@ -327,6 +327,51 @@ int dvq_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, floa
   return launch_gather(E, idx, N, K, D, out, oob, static_cast<cudaStream_t>(stream));
 }
 
+int dvq_vq_backward(const float* z, const float* E, const int64_t* idx, const float* g_zq, const float* g_loss,
+                    const float* rows, int64_t N, int K, int D, float al, float beta, float* dz, float* dE, void* stream) {
+  if (N < 0 || K <= 0 || D <= 0 || (D & 3)) return fail(DVQ_ERR_BAD_SHAPE, "need N >= 0, K > 0, D a positive multiple of 4");
+  if (!g_loss || !rows || (N > 0 && (!z || !E || !idx))) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
+  if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(E) | reinterpret_cast<uintptr_t>(g_zq) |
+       reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dE)) % 16 != 0)
+    return fail(DVQ_ERR_BAD_ALIGN, "dvq_vq_backward needs 16-byte aligned tensors");
+  int rc = require_sm100();
+  if (rc) return rc;
+  return launch_vq_backward(z, E, idx, g_zq, g_loss, rows, N, D, al, beta, dz, dE, static_cast<cudaStream_t>(stream));
+}
+
+int dvq_vq_code_sums(const float* z, const int64_t* idx, int64_t N, int K, int D, float* sums, void* stream) {
+  if (N < 0 || K <= 0 || D <= 0 || (D & 3)) return fail(DVQ_ERR_BAD_SHAPE, "need N >= 0, K > 0, D a positive multiple of 4");
+  if (N > 0 && (!z || !idx || !sums)) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
+  if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(sums)) % 16 != 0)
+    return fail(DVQ_ERR_BAD_ALIGN, "dvq_vq_code_sums needs 16-byte aligned tensors");
+  int rc = require_sm100();
+  if (rc) return rc;
+  return launch_vq_code_sums(z, idx, N, D, sums, static_cast<cudaStream_t>(stream));
+}
+
+int dvq_pcnn_gemm(const DvqPcnnGemm* g, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  return launch_pcnn_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+int dvq_pcnn_embed(const int64_t* x, int x_stride, int W, int B, int Bp, const float* emb, int n_emb, int d, void* img16,
+                   float* img32, void* stream) {
+  if (!x || !emb || !img16) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
+  if (W <= 0 || B <= 0 || Bp < B || Bp % 128 || d <= 0 || d % 8 || n_emb <= 0) return fail(DVQ_ERR_BAD_SHAPE, "need Bp %% 128 == 0, Bp >= B > 0, d %% 8 == 0");
+  int rc = require_sm100();
+  if (rc) return rc;
+  return launch_pcnn_embed(x, x_stride, W, B, Bp, emb, n_emb, d, img16, img32, static_cast<cudaStream_t>(stream));
+}
+
+int dvq_pcnn_rows_to_image(const int64_t* label, int B, int Bp, const float* table, int n_rows, int kd, void* img16, void* stream) {
+  if (!label || !table || !img16) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
+  if (B <= 0 || Bp < B || Bp % 128 || kd <= 0 || kd % 8 || n_rows <= 0) return fail(DVQ_ERR_BAD_SHAPE, "need Bp %% 128 == 0, Bp >= B > 0, kd %% 8 == 0");
+  int rc = require_sm100();
+  if (rc) return rc;
+  return launch_pcnn_rows_to_image(label, B, Bp, table, n_rows, kd, img16, static_cast<cudaStream_t>(stream));
+}
+
 int dvq_debug_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, int ksteps,
                    const uint32_t* strides, uint32_t idesc, int n_cols, float* out, int* err, void* stream) {
   if (!a_img || !b_img || !strides || !out || !err) return fail(DVQ_ERR_BAD_ARG, "NULL argument");

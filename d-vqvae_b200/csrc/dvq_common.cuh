@@ -87,11 +87,20 @@ int launch_vq_refine_binned(const float* z, const float* E, const float* ee, int
 int launch_onehot(const int64_t* idx, int64_t N, int K, float* onehot, cudaStream_t s);
 int launch_finalize(const unsigned long long* hist, const double* sse, int64_t N, int K, int D, float al,
                     float beta, float* loss, float* ppl, cudaStream_t s);
+int launch_vq_backward(const float* z, const float* E, const int64_t* idx, const float* g_zq, const float* g_loss,
+                       const float* rows, int64_t N, int D, float al, float beta, float* dz, float* dE, cudaStream_t s);
+int launch_vq_code_sums(const float* z, const int64_t* idx, int64_t N, int D, float* sums, cudaStream_t s);
 int launch_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, float* out, int* oob,
                   cudaStream_t s);
 
 int launch_umma_probe(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, int ksteps,
                       const uint32_t* strides, uint32_t idesc, int n_cols, float* out, int* err, cudaStream_t s);
+
+// GatedPixelCNN sampler (pcnn_sm100.cu)
+int launch_pcnn_gemm(const DvqPcnnGemm* g, cudaStream_t s);
+int launch_pcnn_embed(const int64_t* x, int x_stride, int W, int B, int Bp, const float* emb, int n_emb, int d, void* img16,
+                      float* img32, cudaStream_t s);
+int launch_pcnn_rows_to_image(const int64_t* label, int B, int Bp, const float* table, int n_rows, int kd, void* img16, cudaStream_t s);
 
 // PointNet
 size_t pointnet_workspace_bytes(int B, int C, int P, int flags);

@@ -79,3 +79,17 @@ def shard_module(module, group=None):
         if isinstance(m, VectorQuantizer):
             m.process_group = group
     return module
+
+
+def world_size(group=None) -> int:
+    return tdist.get_world_size(group if group is not None else tdist.group.WORLD)
+
+
+def all_reduce_sum(t: torch.Tensor, group=None) -> None:
+    tdist.all_reduce(t, op=tdist.ReduceOp.SUM, group=group if group is not None else tdist.group.WORLD)
+
+
+def broadcast0(t: torch.Tensor, group=None) -> None:
+    """Broadcast from the group's rank 0 (replicated state such as re-seeded codebook rows)."""
+    g = group if group is not None else tdist.group.WORLD
+    tdist.broadcast(t, src=tdist.get_global_rank(g, 0), group=g)

@@ -93,8 +93,13 @@ class GatedPixelCNN(nn.Module):
             self.layers.append(GatedMaskedConv2d("A" if i == 0 else "B", dim, 5 if i == 0 else 3, i != 0, n_classes))
         self.output_conv = nn.Sequential(nn.Conv2d(dim, 2048, 1), nn.ReLU(True), nn.Conv2d(2048, input_dim, 1))
         self.apply(_weights_init)
-        self.precision = "fp32"       # "fp32" | "tf32": the sampler's GEMMs (the reference's cuDNN convs are TF32 by default on GPU)
+        # the sampler's contractions: "fp32" / "tf32" = torch GEMMs (the reference's cuDNN convs are TF32 by default on a
+        # GPU); "fp16_tc" = the repo's tcgen05 GEMM kernel with fused epilogues (pixelcnn_tc.py / csrc/pcnn_sm100.cu),
+        # FP16 operands, FP32 accumulation (CUDA only, dim % 256 == 0, input_dim % 256 == 0)
+        self.precision = "fp32"
         self._packed = None
+        self._packed_tc = None
+        self._tc_sampler = None
         self.register_load_state_dict_post_hook(_invalidate_after_load)
 
     # ---- the reference forward, unchanged semantics (models.py:159-173) ---------------------------------
@@ -115,15 +120,29 @@ class GatedPixelCNN(nn.Module):
         ``make_causal`` style) do not bump ``_version`` — call ``invalidate()`` after such an edit (a
         ``load_state_dict`` does it by itself), or set ``repack_every_call = True``."""
         self._packed = None
+        self._packed_tc = None
 
     def _apply(self, fn, *args, **kwargs):
         self._packed = None
+        self._packed_tc = None
+        self._tc_sampler = None
         return super()._apply(fn, *args, **kwargs)
 
     def __getstate__(self):
         d = self.__dict__.copy()
         d["_packed"] = None
+        d["_packed_tc"] = None
+        d["_tc_sampler"] = None
         return d
+
+    def _pack_tc(self):
+        """FP16 weight images for the tcgen05 GEMM kernel; same cache key and invalidation as ``_pack``."""
+        from . import pixelcnn_tc
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (str(next(self.parameters()).device),)
+        if self._packed_tc is not None and self._packed_tc[0] == key and not self.repack_every_call:
+            return self._packed_tc[1]
+        self._packed_tc = (key, pixelcnn_tc.pack_weights(self))
+        return self._packed_tc[1]
 
     def _pack(self):
         """[taps*dim, 2*dim] matrices, masks applied (as make_causal leaves the weights after the first
@@ -158,7 +177,8 @@ class GatedPixelCNN(nn.Module):
 
     def backend_name(self):
         """What executes the sampler's contractions (for benchmark records)."""
-        return {"fp32": "FP32 cuBLAS GEMMs", "tf32": "TF32 cuBLAS GEMMs"}.get(self.precision, self.precision)
+        return {"fp32": "FP32 cuBLAS GEMMs", "tf32": "TF32 cuBLAS GEMMs",
+                "fp16_tc": "tcgen05 GEMM kernel with fused gate / residual epilogues (FP16 operands, FP32 accumulation)"}.get(self.precision, self.precision)
 
     def _matmul_ctx(self):
         if self.precision == "tf32" and torch.cuda.is_available():
@@ -266,12 +286,21 @@ class GatedPixelCNN(nn.Module):
         param = next(self.parameters())
         x = torch.zeros((batch_size, *shape), dtype=torch.int64, device=param.device)
         cache, all_logits = {}, []
+        tc = None
+        if self.precision == "fp16_tc":
+            from . import pixelcnn_tc
+            tc = self._tc_sampler
+            if tc is None or tc.B != batch_size or (tc.H, tc.W) != tuple(shape) or tc.dev != param.device:
+                tc = self._tc_sampler = pixelcnn_tc.TcSampler(self, batch_size, tuple(shape))
+            tc.begin(label)
+        elif self.precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32', 'tf32' or 'fp16_tc'")
         with self._matmul_ctx():
             for i in range(shape[0]):
                 for j in range(shape[1]):
-                    logits = self.step_logits(x, label, i, j, cache)
+                    logits = tc.step_logits(x, i, j) if tc is not None else self.step_logits(x, label, i, j, cache)
                     if return_logits:
-                        all_logits.append(logits)
+                        all_logits.append(logits.clone() if tc is not None else logits)
                     if n_valid is not None:
                         logits = logits.clone()
                         logits[:, n_valid:] = float("-inf")

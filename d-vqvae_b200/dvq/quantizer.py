@@ -81,19 +81,40 @@ class _VQFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_zq, _g_ppl, _g_idx):
         z, weight, idx, n_rows = ctx.saved_tensors
-        flat = z.reshape(-1, weight.shape[1])
-        e = weight.index_select(0, idx.view(-1))
-        scale = 2.0 / (n_rows * weight.shape[1])
-        diff = (flat - e) * scale
+        d = weight.shape[1]
+        want_z, want_e = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_loss is None:
+            g_loss = torch.zeros((), device=z.device)
+        gl = g_loss.detach().to(torch.float32).reshape(1).contiguous()
+        rows = n_rows.reshape(1).contiguous()
+        flat = z.detach().reshape(-1, d)
+        n = flat.shape[0]
+        gq = None
+        if g_zq is not None:
+            gq = g_zq.detach().to(torch.float32).reshape(-1, d).contiguous()
+        if d % 4 == 0 and flat.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0 and (gq is None or gq.data_ptr() % 16 == 0):
+            # one fused pass (dvq_vq_backward): dz written once, dE by vector reductions
+            gz = torch.empty_like(flat) if want_z else None
+            gw = torch.zeros_like(weight) if want_e else None
+            with torch.cuda.device(z.device):
+                _cabi.check(_cabi.lib.dvq_vq_backward(
+                    flat.data_ptr(), weight.detach().data_ptr(), idx.data_ptr(), gq.data_ptr() if gq is not None else None,
+                    gl.data_ptr(), rows.data_ptr(), n, weight.shape[0], d, ctx.al, ctx.beta,
+                    gz.data_ptr() if gz is not None else None, gw.data_ptr() if gw is not None else None,
+                    _stream_ptr(z.device)), "dvq_vq_backward")
+            return (gz.view_as(z) if gz is not None else None), gw, None
+        # shapes the vector kernel does not take (e_dim not a multiple of 4, odd storage offsets): same formulas in torch
+        e = weight.detach().index_select(0, idx.view(-1))
+        diff = (flat - e) * (2.0 / (rows * d))
         gz = gw = None
-        if ctx.needs_input_grad[0]:
-            gz = (g_loss * ctx.al) * diff
-            if g_zq is not None:
-                gz = gz + g_zq.reshape_as(flat)
+        if want_z:
+            gz = (gl * ctx.al) * diff
+            if gq is not None:
+                gz = gz + gq
             gz = gz.view_as(z)
-        if ctx.needs_input_grad[1]:
+        if want_e:
             gw = torch.zeros_like(weight)
-            gw.index_add_(0, idx.view(-1), (-(g_loss * ctx.beta)) * diff)
+            gw.index_add_(0, idx.view(-1), (-(gl * ctx.beta)) * diff)
         return gz, gw, None
 
 
@@ -221,6 +242,63 @@ class VectorQuantizer(nn.Module):
         else:
             enc = LazyOneHot(idx, self.n_e)
         return loss, z_q, ppl, enc, idx
+
+    # ------------------------------------------------------------------ training hooks (SURVEY §8f-3)
+    # The reference trains its codebooks through the loss alone (quantizer.py:56-57).  These hooks are the usual
+    # companions of a VQ bottleneck and run on what the fused forward already produced: the (all-reduced) usage
+    # histogram in ``last_stats`` and the indices; the per-code input sums come from one scatter-add kernel.
+    def code_sums(self, z, idx):
+        """[n_e, e_dim] sum of the latents assigned to each code (``dvq_vq_code_sums``); summed over the ranks of a
+        row-sharded module."""
+        flat = z.detach().reshape(-1, self.e_dim).contiguous()
+        if self.e_dim % 4 != 0 or flat.data_ptr() % 16 != 0:
+            sums = torch.zeros(self.n_e, self.e_dim, device=flat.device)
+            sums.index_add_(0, idx.view(-1), flat)
+        else:
+            sums = torch.zeros(self.n_e, self.e_dim, device=flat.device)
+            with torch.cuda.device(flat.device):
+                _cabi.check(_cabi.lib.dvq_vq_code_sums(flat.data_ptr(), idx.contiguous().data_ptr(), flat.shape[0], self.n_e,
+                                                       self.e_dim, sums.data_ptr(), _stream_ptr(flat.device)), "dvq_vq_code_sums")
+        if self.process_group is not None and _dist.world_size(self.process_group) > 1:
+            _dist.all_reduce_sum(sums, self.process_group)
+        return sums
+
+    @torch.no_grad()
+    def ema_update(self, z, idx, decay: float = 0.99, eps: float = 1e-5):
+        """Exponential-moving-average codebook update fed by the last forward's histogram (global on a row-sharded
+        module): cluster_size <- decay * cluster_size + (1 - decay) * hist; ema_w <- decay * ema_w + (1 - decay) * sums;
+        embedding <- ema_w / laplace-smoothed cluster_size.  State lives in (non-persistent) buffers created on first use."""
+        hist = self.last_stats[:self.n_e].to(torch.float32)
+        sums = self.code_sums(z, idx)
+        if not hasattr(self, "ema_cluster_size"):
+            self.register_buffer("ema_cluster_size", torch.zeros(self.n_e, device=hist.device), persistent=False)
+            self.register_buffer("ema_w", self.embedding.weight.detach().clone(), persistent=False)
+        self.ema_cluster_size.mul_(decay).add_(hist, alpha=1.0 - decay)
+        self.ema_w.mul_(decay).add_(sums, alpha=1.0 - decay)
+        total = self.ema_cluster_size.sum()
+        smoothed = (self.ema_cluster_size + eps) / (total + self.n_e * eps) * total
+        self.embedding.weight.copy_(self.ema_w / smoothed.unsqueeze(1))
+        return hist
+
+    @torch.no_grad()
+    def reset_unused_codes(self, z, min_usage: int = 1, generator=None):
+        """Re-seed the codes the last forward used fewer than ``min_usage`` times (global histogram) with latents
+        drawn from ``z``; on a row-sharded module rank 0's draw is broadcast so the replicas stay identical.
+        Returns the number of codes reset (a host int: this hook synchronises)."""
+        hist = self.last_stats[:self.n_e]
+        dead = (hist < min_usage).nonzero().view(-1)
+        if dead.numel() == 0:
+            return 0
+        flat = z.detach().reshape(-1, self.e_dim)
+        pick = torch.randint(0, flat.shape[0], (dead.numel(),), device=flat.device, generator=generator)
+        new_rows = flat[pick].contiguous()
+        if self.process_group is not None and _dist.world_size(self.process_group) > 1:
+            _dist.broadcast0(new_rows, self.process_group)
+        self.embedding.weight[dead] = new_rows
+        if hasattr(self, "ema_w"):
+            self.ema_w[dead] = new_rows
+            self.ema_cluster_size[dead] = float(min_usage)
+        return int(dead.numel())
 
     def get_emb(self, min_encoding_indices, dim):
         """quantizer.py:68-75: index -> embedding.  Returns ``[B, dim]`` (``[1, dim]`` for the

@@ -117,6 +117,19 @@ DVQ_API int dvq_vq_read_counters(const void* workspace, int64_t N, int K, int D,
 DVQ_API int dvq_vq_finalize(const unsigned long long* hist, const double* sse, int64_t N_total, int K, int D,
                     float al, float beta, float* loss, float* perplexity, void* stream);
 
+/* Backward of the forward above — the autograd graph of quantizer.py:56-60 (loss = al*mean((sg[z_q]-z)^2) +
+ * beta*mean((z_q-sg[z])^2), z_q_out = z + sg[z_q - z]):
+ *   dz[n,:]       = g_zq[n,:] + g_loss * al   * 2/(rows*D) * (z[n,:] - E[idx[n],:])     (dz may be NULL)
+ *   dE[idx[n],:] +=             g_loss * beta * 2/(rows*D) * (E[idx[n],:] - z[n,:])     (dE may be NULL; zero it first)
+ * g_loss [1] and rows [1] are DEVICE floats (rows = number of rows the loss was averaged over: N, or the
+ * all-reduced histogram total on a row-sharded run); g_zq may be NULL (no gradient reaches z_q).  D % 4 == 0. */
+DVQ_API int dvq_vq_backward(const float* z, const float* E, const int64_t* idx, const float* g_zq, const float* g_loss,
+                    const float* rows, int64_t N, int K, int D, float al, float beta, float* dz, float* dE, void* stream);
+
+/* sums[k,:] += sum of the rows z[n,:] with idx[n] == k — the per-code input sums of an EMA codebook update
+ * (together with the usage histogram of dvq_vq_forward).  sums [K,D] must be zeroed by the caller.  D % 4 == 0. */
+DVQ_API int dvq_vq_code_sums(const float* z, const int64_t* idx, int64_t N, int K, int D, float* sums, void* stream);
+
 /* VectorQuantizer.get_emb — quantizer.py:68-75 (batched meaning: out[n,:] = E[idx[n],:]).
  * Out-of-range indices set *oob (device int, may be NULL) and write zeros. */
 DVQ_API int dvq_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, float* out, int* oob, void* stream);
@@ -124,6 +137,43 @@ DVQ_API int dvq_gather(const float* E, const int64_t* idx, int64_t N, int K, int
 /* min_encodings — quantizer.py:40-42: out[n,k] = (k == idx[n]) as fp32, every element written
  * once (no memset + scatter).  Separate entry so the [N,K] matrix can be produced on demand. */
 DVQ_API int dvq_onehot(const int64_t* idx, int64_t N, int K, float* out, void* stream);
+
+/* ---- GatedPixelCNN prior: tcgen05 GEMM with fused epilogues (network/pixelcnn/models.py:65-88,176-197) ----------
+ * C[m,n] = sum_s A_s[m + 128*tile_shift_s, :] . W_s[:, n], FP16 operands, FP32 accumulation.  Activations are FP16
+ * operand images: rows in tiles of 128, a tile stored [K/8][128][8 halfs]; weights are images [n/256][K/8][256][8].
+ * A grid row's rows are ordered column-major (m = column * B + b), so a convolution tap is a K-segment with a
+ * whole-tile shift; a segment is skipped for tiles whose grid column + col_shift falls outside [0, ncols_src).
+ * mode 0 GATE: 128 'a' + 128 'b' columns per tile, out = tanh(a + bias + cond_a) * sigmoid(b + bias + cond_b) -> FP16 image
+ *   (out_kd = d wide) and, if pre_img, the raw a|b pre-activations (+ bias) -> FP16 image (2 d wide); cond_img: FP16 image
+ *   [B, 2 d] of the class-conditional rows (may be NULL); d_gate = d.
+ * mode 1 RES: acc + bias (+ res_img if res_in) -> res_img (FP32 image [K/4][128][4]) and out_img (FP16 image).
+ * mode 2 RELU: relu(acc + bias) -> out_img.   mode 3 LOGITS: acc + bias -> logits, row-major [m_tiles*128, n_tiles*256].
+ * bias holds n_tiles * 256 floats in tile column order.  *err (device int, may be NULL) is set on a pipeline time-out. */
+typedef struct DvqPcnnSeg {
+  const void* a_img;
+  const void* w_img;
+  int a_kd, ks, tile_shift, col_shift;
+} DvqPcnnSeg;
+typedef struct DvqPcnnGemm {
+  DvqPcnnSeg seg[12];
+  int nseg, m_tiles, n_tiles, tiles_per_col, ncols_src, mode;
+  const float* bias;
+  const void* cond_img;
+  void* out_img;
+  void* pre_img;
+  float* res_img;
+  float* logits;
+  int out_kd, res_in, d_gate;
+  int* err;
+} DvqPcnnGemm;
+DVQ_API int dvq_pcnn_gemm(const DvqPcnnGemm* g, void* stream);
+/* x[b * x_stride + c] (int64 indices of one grid row, c < W) -> emb rows as FP16 image (and FP32 image if img32),
+ * rows m = c * Bp + b, Bp a multiple of 128 (rows b >= B are zero). */
+DVQ_API int dvq_pcnn_embed(const int64_t* x, int x_stride, int W, int B, int Bp, const float* emb, int n_emb, int d,
+                           void* img16, float* img32, void* stream);
+/* table[label[b], :] (FP32 [n_rows, kd]) -> FP16 image [Bp, kd]. */
+DVQ_API int dvq_pcnn_rows_to_image(const int64_t* label, int B, int Bp, const float* table, int n_rows, int kd,
+                                   void* img16, void* stream);
 
 /* Host-buffer (end-to-end) form of the same forward: z_host/E_host/zq_host/idx_host are
  * HOST pointers (pinned for full overlap).  Rows are streamed through the GPU in chunks on

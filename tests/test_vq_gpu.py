@@ -472,3 +472,53 @@ def test_streamed_kernel_variants_behind_env_switches(env):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET, root], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "VARIANT_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_backward_kernel_sharded_scale_and_ema_hooks():
+    """dvq_vq_backward with a row count that is NOT the local N (the row-sharded case: the loss is a mean over the
+    global rows), dvq_vq_code_sums, and the EMA / usage-reset hooks against their torch restatements."""
+    import dvq
+    from dvq import _cabi
+    z, E, al, beta = vq_inputs("vq_k512_d64")
+    m = _module(E, al, beta, 0)
+    zt = torch.from_numpy(z).cuda()
+    with torch.no_grad():
+        loss, zq, ppl, enc, idx = m(zt, True)
+    flat_idx = idx.view(-1)
+    e = m.embedding.weight.detach()[flat_idx]
+    # --- backward kernel, rows = 3 * N (as if two more equal shards existed)
+    gz = torch.empty_like(zt)
+    gw = torch.zeros_like(m.embedding.weight)
+    g_zq = torch.randn_like(zt)
+    gl = torch.tensor([1.7], device="cuda")
+    rows = torch.tensor([3.0 * zt.shape[0]], device="cuda")
+    _cabi.check(_cabi.lib.dvq_vq_backward(zt.data_ptr(), m.embedding.weight.data_ptr(), idx.data_ptr(), g_zq.data_ptr(), gl.data_ptr(),
+                                          rows.data_ptr(), zt.shape[0], 512, 64, al, beta, gz.data_ptr(), gw.data_ptr(), None), "bwd")
+    scale = 2.0 * 1.7 / (3.0 * zt.shape[0] * 64)
+    assert torch.allclose(gz, g_zq + scale * al * (zt - e), rtol=1e-5, atol=1e-8)
+    ref_gw = torch.zeros_like(gw).index_add_(0, flat_idx, scale * beta * (e - zt))
+    assert torch.allclose(gw, ref_gw, rtol=1e-4, atol=1e-9)
+    # --- code sums + EMA step
+    sums = m.code_sums(zt, idx)
+    ref_sums = torch.zeros(512, 64, device="cuda").index_add_(0, flat_idx, zt)
+    assert torch.allclose(sums, ref_sums, rtol=1e-5, atol=1e-6)
+    w0 = m.embedding.weight.detach().clone()
+    hist = m.ema_update(zt, idx, decay=0.9, eps=1e-5)
+    cs = 0.1 * hist
+    ew = 0.9 * w0 + 0.1 * ref_sums
+    tot = cs.sum()
+    ref_w = ew / (((cs + 1e-5) / (tot + 512 * 1e-5) * tot).unsqueeze(1))
+    assert torch.allclose(m.embedding.weight.detach(), ref_w, rtol=1e-5, atol=1e-7)
+    # --- usage reset: a codebook with far-away rows that no latent selects
+    E2 = E.copy()
+    E2[100:110] += 50.0
+    m2 = _module(E2, al, beta, 0)
+    with torch.no_grad():
+        m2(zt, True)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n_reset = m2.reset_unused_codes(zt, min_usage=1, generator=g)
+    assert n_reset >= 10
+    assert float(m2.embedding.weight.detach()[100:110].abs().max()) < 10.0
+    with torch.no_grad():
+        m2(zt, True)
+    assert int((m2.last_stats[100:110] > 0).sum()) == 10            # the re-seeded codes are latents now: each is used
