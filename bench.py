@@ -287,17 +287,25 @@ def run_secondary(torch, tdist, dvq, dev, rank, world, fence):
         net = dvq.GraspGenerator().to(dev).eval().requires_grad_(False)
         torch.manual_seed(1)
         pcnn = GatedPixelCNN(512, 512, 15).to(dev).eval().requires_grad_(False)
-        pcnn.precision = "tf32"
+        pcnn.precision = "fp16_tc"                          # the repo's tcgen05 GEMM kernel (csrc/pcnn_sm100.cu)
         net.prior = pixelcnn_prior(pcnn, n_valid=128)
         ms = timed(lambda: net.gen(obj))
-        flop = B * world * (2 * P * 558080.0 + 778 * (2 * (3 * 64 + 64 * 128 + 128 * 1024) * 2.0) + 5.8e9)
+        ms_sampler = timed(lambda: pcnn.generate(None, torch.zeros(B, dtype=torch.int64, device=dev), batch_size=B, n_valid=128))
+        try:
+            ms_graph = timed(lambda: net.gen_graphed(obj))
+        except Exception as e:                              # noqa: BLE001
+            ms_graph = None
+        pcnn_flop = float(pcnn._tc_sampler.flops)             # tensor-core flops of one sample grid of B grasps, counted per launch
+        flop = world * (B * (2 * P * 558080.0 + 778 * (2 * (3 * 64 + 64 * 128 + 128 * 1024) * 2.0)) + pcnn_flop)
         out["grasp_generation_b4096"] = {
             "metric": "grasps_per_sec", "value": B * world / (ms * 1e-3), "unit": "grasps/s", "ms_per_batch": ms, "batch_per_gpu": B, "points": P,
             "prior": "GatedPixelCNN(512,512,15), exact row-cached sampler, %s, random init, 128 valid classes" % pcnn.backend_name(),
-            "hand_layer": "linear stub (MANO assets need chumpy: absent)",
+            "hand_layer": "linear stub (MANO assets need chumpy: absent)", "pixelcnn_sampler_ms": ms_sampler,
+            "ms_per_batch_cuda_graph": ms_graph,
             "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": bf16_sus * world, "unit": "TFLOP/s",
                          "frac": flop / (ms * 1e-3) / 1e12 / (bf16_sus * world),
-                         "what": "PointNets 3.78 GFLOP + row-cached PixelCNN sampler ~5.8 GFLOP per grasp over the sustained BF16 peak x GPUs"}}
+                         "pixelcnn_gflop_per_grasp": pcnn_flop / B / 1e9, "pixelcnn_sampler_tflops": pcnn_flop / (ms_sampler * 1e-3) / 1e12,
+                         "what": "PointNets 3.78 GFLOP per grasp + the row-cached PixelCNN sampler's issued GEMM flops (counted per launch) over the sustained BF16 peak x GPUs"}}
     except Exception as e:                                  # noqa: BLE001
         out["grasp_generation_b4096"] = {"error": repr(e)}
     return out

@@ -349,6 +349,19 @@ int dvq_vq_code_sums(const float* z, const int64_t* idx, int64_t N, int K, int D
   return launch_vq_code_sums(z, idx, N, D, sums, static_cast<cudaStream_t>(stream));
 }
 
+int dvq_gather_multi(const float* const* E, int G, const int64_t* codes, int64_t N, int K, int D, float* out, int64_t out_stride,
+                     int* oob, void* stream) {
+  if (G <= 0 || G > 8 || N < 0 || K <= 0 || D <= 0 || (D & 3) || out_stride < (int64_t)G * D || (out_stride & 3))
+    return fail(DVQ_ERR_BAD_SHAPE, "need 1 <= G <= 8, D %% 4 == 0, out_stride >= G * D and a multiple of 4");
+  if (!E || (N > 0 && (!codes || !out))) return fail(DVQ_ERR_BAD_ARG, "NULL argument");
+  for (int g = 0; g < G; ++g)
+    if (!E[g] || reinterpret_cast<uintptr_t>(E[g]) % 16) return fail(DVQ_ERR_BAD_ALIGN, "codebook %d is NULL or not 16-byte aligned", g);
+  if (reinterpret_cast<uintptr_t>(out) % 16) return fail(DVQ_ERR_BAD_ALIGN, "out needs 16-byte alignment");
+  int rc = require_sm100();
+  if (rc) return rc;
+  return launch_gather_multi(E, G, codes, N, K, D, out, out_stride, oob, static_cast<cudaStream_t>(stream));
+}
+
 int dvq_pcnn_gemm(const DvqPcnnGemm* g, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;

@@ -89,6 +89,8 @@ int launch_finalize(const unsigned long long* hist, const double* sse, int64_t N
                     float beta, float* loss, float* ppl, cudaStream_t s);
 int launch_vq_backward(const float* z, const float* E, const int64_t* idx, const float* g_zq, const float* g_loss,
                        const float* rows, int64_t N, int D, float al, float beta, float* dz, float* dE, cudaStream_t s);
+int launch_gather_multi(const float* const* E, int G, const int64_t* codes, int64_t N, int K, int D, float* out, int64_t out_stride,
+                        int* oob, cudaStream_t s);
 int launch_vq_code_sums(const float* z, const int64_t* idx, int64_t N, int D, float* sums, cudaStream_t s);
 int launch_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, float* out, int* oob,
                   cudaStream_t s);

@@ -133,6 +133,29 @@ __global__ void vq_backward_kernel(const float* __restrict__ z, const float* __r
   }
 }
 
+// Grouped get_emb (gen_net.py:101-106: six part codebooks, one index each): out[n, g * D .. g * D + D) = E_g[codes[n, g], :]
+// for every group in ONE launch, written straight into the concatenated decoder input (row pitch out_stride floats).
+struct GatherMultiParams {
+  const float* E[8];
+  int G;
+};
+__global__ void gather_multi_kernel(const GatherMultiParams gp, const int64_t* __restrict__ codes, int64_t N, int K, int D,
+                                    float* __restrict__ out, int64_t out_stride, int* __restrict__ oob) {
+  const int nv = D >> 2;
+  const int64_t total = N * gp.G * (int64_t)nv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nv) << 2;
+    const int64_t ng = i / nv;
+    const int g = (int)(ng % gp.G);
+    const int64_t n = ng / gp.G;
+    const int64_t k = __ldg(codes + n * gp.G + g);
+    const bool ok = k >= 0 && k < K;
+    if (!ok && oob) atomicExch(oob, 1);
+    const float4 v = ok ? ldg4(gp.E[g] + k * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(out + n * out_stride + (int64_t)g * D + c) = v;
+  }
+}
+
 // sums[k,:] += sum over the rows assigned to code k of z[n,:]  (the per-code input sums of an EMA codebook update)
 __global__ void vq_code_sums_kernel(const float* __restrict__ z, const int64_t* __restrict__ idx, int64_t N, int D,
                                     float* __restrict__ sums) {
@@ -160,6 +183,24 @@ int launch_vq_backward(const float* z, const float* E, const int64_t* idx, const
   else if (dz) { if (g_zq) DVQ_BWD(true, true, false); else DVQ_BWD(false, true, false); }
   else DVQ_BWD(false, false, true);
 #undef DVQ_BWD
+  DVQ_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return DVQ_OK;
+}
+
+int launch_gather_multi(const float* const* E, int G, const int64_t* codes, int64_t N, int K, int D, float* out, int64_t out_stride,
+                        int* oob, cudaStream_t s) {
+  if (N == 0) return DVQ_OK;
+  DeviceProps dp;
+  int rc = device_props(&dp);
+  if (rc) return rc;
+  GatherMultiParams gp;
+  gp.G = G;
+  for (int g = 0; g < 8; ++g) gp.E[g] = g < G ? E[g] : nullptr;
+  const int threads = 256;
+  int64_t blocks = (N * G * (D / 4) + threads - 1) / threads;
+  if (blocks > (int64_t)dp.sm_count * 16) blocks = (int64_t)dp.sm_count * 16;
+  gather_multi_kernel<<<(unsigned)blocks, threads, 0, s>>>(gp, codes, N, K, D, out, out_stride, oob);
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return DVQ_OK;

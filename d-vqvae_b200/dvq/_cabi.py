@@ -47,6 +47,7 @@ SYMBOLS = {
     "dvq_pcnn_embed": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "dvq_pcnn_rows_to_image": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     "dvq_gather": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "dvq_gather_multi": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp]),
     "dvq_onehot": (_i, [_vp, _i64, _i, _vp, _vp]),
     "dvq_host_ctx_create": (_i, [_i64, _i, _i, C.POINTER(_vp)]),
     "dvq_host_ctx_destroy": (_i, [_vp]),

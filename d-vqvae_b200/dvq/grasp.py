@@ -17,6 +17,9 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+import ctypes as C
+
+from . import _cabi
 from .pointnet import PointNetEncoder
 from .vqvae import VQVAE
 
@@ -86,6 +89,31 @@ class GraspGenerator(nn.Module):
         self.pos_decoder = Decoder([1024, 128, 6], 2048)                                                # :32-33
         self.prior = prior if prior is not None else uniform_prior(128)
         self.hand_layer = hand_layer if hand_layer is not None else LinearHandStub()
+        self._graph = None
+
+    @torch.no_grad()
+    def gen_graphed(self, obj):
+        """``gen`` replayed from a CUDA graph (captured on first use per input shape): the ~550 kernel launches of a
+        batch — PointNets, VQ lookup, the PixelCNN sampler's GEMMs, softmax / multinomial, grouped gather, decoder MLPs —
+        become one graph launch.  The prior must draw from torch's default CUDA generator (``pixelcnn_prior`` does);
+        returns the graph's static output tensors (overwritten by the next call)."""
+        key = (tuple(obj.shape), str(obj.device))
+        if self._graph is None or self._graph[0] != key:
+            static_in = obj.clone()
+            side = torch.cuda.Stream(device=obj.device)
+            side.wait_stream(torch.cuda.current_stream(obj.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):                     # warm-up: workspaces, weight caches, kernel attributes
+                    self.gen(static_in)
+            torch.cuda.current_stream(obj.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.gen(static_in)
+            self._graph = (key, graph, static_in, out)
+        _, graph, static_in, out = self._graph
+        static_in.copy_(obj)
+        graph.replay()
+        return out
 
     @torch.no_grad()
     def gen(self, obj):
@@ -95,8 +123,18 @@ class GraspGenerator(nn.Module):
         feat_pos, _, _ = self.obj_encoder_pos(obj)                         # :82
         idx6, obj_emb = self.vqvae6.inference(feat_type)                   # :83
         codes = self.prior(idx6.view(B), B)                                # :88-100
-        embs = [getattr(self, "vqvae%d" % i).get_embbeding(codes[:, i].contiguous(), 256) for i in range(6)]   # :101-106
-        recon = self.decoder(torch.cat(embs + [feat_type], dim=1)).contiguous().view(B, 55)             # :109-113
+        # :101-106 + the torch.cat of :109 — six get_embbeding calls as ONE grouped gather that writes the decoder input
+        z_out = torch.empty((B, 6 * 256 + 1024), dtype=torch.float32, device=obj.device)
+        books = [getattr(self, "vqvae%d" % i).vector_quantization.embedding.weight.detach() for i in range(6)]
+        ptrs = (C.c_void_p * 6)(*[w.data_ptr() for w in books])
+        codes = codes.to(torch.int64).contiguous()
+        oob = torch.zeros(1, dtype=torch.int32, device=obj.device)
+        with torch.cuda.device(obj.device):
+            _cabi.check(_cabi.lib.dvq_gather_multi(ptrs, 6, codes.data_ptr(), B, books[0].shape[0], 256, z_out.data_ptr(), z_out.shape[1],
+                                                   oob.data_ptr(), torch.cuda.current_stream(obj.device).cuda_stream), "dvq_gather_multi")
+        torch._assert_async(oob[0] == 0, "dvq.GraspGenerator: part-code index out of range")
+        z_out[:, 6 * 256:] = feat_type
+        recon = self.decoder(z_out).contiguous().view(B, 55)               # :109-113
         verts = self.hand_layer(recon[:, :10], recon[:, 10:55])            # :117-118
         hand_feat, _, _ = self.recon_encoder(verts.permute(0, 2, 1))       # :120
         recon_pos = self.pos_decoder(torch.cat([hand_feat, feat_pos], dim=1)).contiguous().view(B, 6)   # :121-123

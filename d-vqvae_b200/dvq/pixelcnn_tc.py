@@ -118,9 +118,11 @@ class TcSampler:
         self.logits = torch.empty((self.Bp, model.input_dim), dtype=torch.float32, device=dev)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.cond = [h16(self.Bp * 2 * d) for _ in range(L)]
+        self.flops = 0          # 2 * M * K * N issued to the tensor cores since begin() (padded rows included)
 
     def begin(self, label: torch.Tensor):
         """Start a new sample grid: current weight images, class-conditional rows of this batch's labels."""
+        self.flops = 0
         self.packs = self.m._pack_tc()
         label = label.to(self.dev).to(torch.int64).contiguous()
         with torch.cuda.device(self.dev):
@@ -139,6 +141,9 @@ class TcSampler:
             g.seg[i].a_img, g.seg[i].w_img = a_ptr, w.data_ptr()
             g.seg[i].a_kd, g.seg[i].ks, g.seg[i].tile_shift, g.seg[i].col_shift = a_kd, ks, col_shift * self.T, col_shift
         g.nseg, g.m_tiles, g.n_tiles, g.tiles_per_col, g.ncols_src, g.mode = len(segs), m_tiles, n_tiles, self.T, ncols_src, mode
+        for c in range(m_tiles // self.T):       # accounting: the segments the kernel runs for the tiles of grid column c
+            k_valid = sum(ks for (_, _, _, ks, sh) in segs if 0 <= c + sh < ncols_src)
+            self.flops += 2 * (self.T * 128) * k_valid * (n_tiles * 256)
         g.bias = bias.data_ptr()
         g.cond_img = cond.data_ptr() if cond is not None else None
         g.out_img = out.data_ptr() if out is not None else None

@@ -134,6 +134,12 @@ DVQ_API int dvq_vq_code_sums(const float* z, const int64_t* idx, int64_t N, int 
  * Out-of-range indices set *oob (device int, may be NULL) and write zeros. */
 DVQ_API int dvq_gather(const float* E, const int64_t* idx, int64_t N, int K, int D, float* out, int* oob, void* stream);
 
+/* Grouped get_emb for the six part codebooks of GenNet.gen (gen_net.py:101-106) in ONE launch:
+ * out[n, g*D .. g*D+D) = E[g][codes[n*G + g], :], row pitch out_stride floats (the concatenated decoder input, :109).
+ * E: host array of G <= 8 device pointers to [K,D] codebooks.  Out-of-range codes set *oob and write zeros. */
+DVQ_API int dvq_gather_multi(const float* const* E, int G, const int64_t* codes, int64_t N, int K, int D, float* out,
+                     int64_t out_stride, int* oob, void* stream);
+
 /* min_encodings — quantizer.py:40-42: out[n,k] = (k == idx[n]) as fp32, every element written
  * once (no memset + scatter).  Separate entry so the [N,K] matrix can be produced on demand. */
 DVQ_API int dvq_onehot(const int64_t* idx, int64_t N, int K, float* out, void* stream);

@@ -30,7 +30,7 @@ for m in (net.obj_encoder_type, net.obj_encoder_pos, net.recon_encoder):
     m.precision = os.environ.get("PN_PRECISION", "fp16_tc")
 torch.manual_seed(1)
 pcnn = GatedPixelCNN(512, 512, 15).to(dev).eval()
-pcnn.precision = "tf32"
+pcnn.precision = os.environ.get("PCNN_PRECISION", "fp16_tc")
 net.prior = pixelcnn_prior(pcnn, n_valid=128)
 
 # this rank's objects: contiguous shard of the N_OBJ clouds (seeded per object block so any world size sees the same set)

@@ -46,3 +46,28 @@ def test_grasp_state_dict_names_follow_reference():
     for k in ("obj_encoder_type.stn.conv1.weight", "vqvae0.vector_quantization.embedding.weight", "vqvae6.vector_quantization.embedding.weight",
               "decoder.MLP.L0.weight", "decoder.MLP.L2.bias", "recon_encoder.bn3.running_var", "pos_decoder.MLP.L1.weight"):
         assert k in keys, k
+
+
+def test_grouped_gather_and_graphed_generation():
+    """dvq_gather_multi == six get_embbeding calls; gen_graphed (one CUDA-graph launch per batch) == gen for the
+    deterministic stages, with the kernel-backed PixelCNN prior."""
+    import dvq
+    from dvq.grasp import pixelcnn_prior
+    from dvq.pixelcnn import GatedPixelCNN
+    torch.manual_seed(0)
+    pcnn = GatedPixelCNN(512, 256, 2, 128).cuda().eval().requires_grad_(False)
+    pcnn.precision = "fp16_tc"
+    net = dvq.GraspGenerator(prior=pixelcnn_prior(pcnn, n_valid=128)).cuda().eval().requires_grad_(False)
+    obj = 0.1 * torch.randn(130, 4, 500, device="cuda")
+    recon, pos = net.gen(obj)
+    L = net.last
+    embs = [getattr(net, "vqvae%d" % i).get_embbeding(L["codes"][:, i].contiguous(), 256) for i in range(6)]
+    z_ref = torch.cat(embs + [L["feat_type"]], dim=1)
+    assert torch.allclose(net.decoder(z_ref).view(130, 55), recon, rtol=1e-5, atol=1e-6)
+    r2, p2 = net.gen_graphed(obj)
+    L2 = net.last
+    assert torch.equal(L2["feat_type"], L["feat_type"]) and torch.equal(L2["idx6"], L["idx6"])     # stages before the sampler
+    assert r2.shape == recon.shape and torch.isfinite(r2).all() and torch.isfinite(p2).all()
+    r3, _ = net.gen_graphed(obj * 1.01)                    # replay with new input contents
+    assert torch.isfinite(r3).all()
+    pcnn._tc_sampler.check()
