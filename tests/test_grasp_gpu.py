@@ -71,3 +71,41 @@ def test_grouped_gather_and_graphed_generation():
     r3, _ = net.gen_graphed(obj * 1.01)                    # replay with new input contents
     assert torch.isfinite(r3).all()
     pcnn._tc_sampler.check()
+
+
+def _fixed_prior(codes):
+    def prior(idx6, batch):
+        g = torch.from_numpy(codes).to(idx6.device)
+        return torch.stack([g[:, 0, 1], g[:, 0, 2], g[:, 1, 1], g[:, 1, 2], g[:, 2, 1], g[:, 2, 2]], dim=1)
+    return prior
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("fp16_tc", 5e-3)])
+def test_generation_graph_matches_the_real_reference_gen(precision, tol):
+    """tests/golden/gennet_stages.npz holds the outputs of the REAL reference's GenNet.gen (network/gen_net.py:78-125,
+    run on CPU by oracle/gen_golden_gennet.py with these weights, fixed prior codes and the linear hand stub), one
+    object at a time (reference semantics B = 1).  The batched B200 graph must reproduce them: object-codebook index
+    exactly, the 55 hand parameters and the 6-DoF pose within `tol` of their scale."""
+    import hashlib
+    import dvq
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "gennet_stages.npz"))
+    torch.manual_seed(0)
+    net = dvq.GraspGenerator()
+    h = hashlib.sha256()
+    for k, v in sorted(net.state_dict().items()):
+        h.update(k.encode())
+        h.update(v.detach().cpu().numpy().tobytes())
+    if h.hexdigest() != str(g["sd_sha256"]):
+        pytest.skip("torch CPU RNG stream differs from the build container")
+    net.prior = _fixed_prior(g["codes"])
+    net = net.cuda().eval().requires_grad_(False)
+    for m in (net.obj_encoder_type, net.obj_encoder_pos, net.recon_encoder):
+        m.precision = precision
+    obj = torch.from_numpy(po.make_cloud(int(g["cloud_seed"]), 3, 4, 3000)).cuda()
+    recon, pos = net.gen(obj)                                     # all three objects in ONE batch
+    L = net.last
+    fscale = float(np.abs(g["feat_type"]).max())
+    assert np.abs(L["feat_type"].cpu().numpy() - g["feat_type"]).max() <= tol * fscale
+    assert np.array_equal(L["idx6"].cpu().numpy().reshape(-1), g["idx6"])
+    assert np.abs(recon.cpu().numpy() - g["recon"]).max() <= tol * max(1.0, float(np.abs(g["recon"]).max()))
+    assert np.abs(pos.cpu().numpy() - g["recon_pos"]).max() <= tol * max(1.0, float(np.abs(g["recon_pos"]).max()))
