@@ -526,8 +526,12 @@ __device__ __forceinline__ void filter_subchunk(uint32_t (&v)[32], int col0, uin
   if (st.m1 - m1n > band) { st.cnt = -1; st.cand = 0u; st.ncand = 0; }
   st.m1 = m1n;
   const float TB = fmaf(m1n, BIG, band_big);   // == (m1 + band) * 2^20: scaling by a power of two commutes with the rounding
+#ifdef DVQ_KO_IND   // knock-out: no indicator pass — every row "decided" for the first code of its minimum's sub-chunk
+  const uint32_t bits = (m <= m1n) ? 0x80000000u : 0u; (void)TB;
+#else
   const uint32_t bits = subchunk_bits(key, TB);
   st.cnt += __popc(bits);
+#endif
   if (bits) { cand_push<LIST>(st, gbit); st.bits = bits; st.col0 = col0; }   // the position is decoded once per row
 }
 
@@ -798,6 +802,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 #pragma unroll
               for (int j = 0; j < nk; ++j) {   // zh . eh, one slice
                 tc::umma_f16(d_tmem, ad, bd, idesc, acc);
+#ifdef DVQ_KO_MMA2   // timing model of a half-rate MMA kind (kind::tf32 straight from the staged fp32 tile): every k-step twice
+                tc::umma_f16(d_tmem, ad, bd, idesc, 1);
+#endif
                 acc = 1; ad += a_step; bd += b_step;
               }
               if (USE_ZL) {   // single-slice shapes only (see vq_tc_supported)
@@ -874,7 +881,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), L.nstage == 2 ? (js >> 1) & 1u : js & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
         if (warp == CONV_WARP0) TRACE(3, 0, 0);
         const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nvs;
+#ifdef DVQ_KO_NORM   // knock-out (timing experiment, wrong results): skip the norm pass
+        if (r < rows) nsq = 64.f;
+        if (false) {
+#else
         if (r < rows) {
+#endif
           // two packed (FFMA2) accumulator pairs: half the issued instructions and four short dependency chains
           uint64_t n01 = pack_f32x2(0.f, 0.f), n23 = n01;
           for (int i = 0; i < nvs; ++i) {
@@ -919,7 +931,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
         if (ns > 1) { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), L.nstage == 2 ? (js >> 1) & 1u : js & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
         const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nvs;
         uint8_t* aslice = aimg + (size_t)(sl * (nvs / 2)) * A_CHUNK_BYTES;
+#ifdef DVQ_KO_CONV   // knock-out: skip the FP16 conversion of the tile (the A image keeps stale data)
+        for (int i = 0; i < 0; ++i) {
+#else
         for (int i = 0; i < nvs / 2; ++i) {
+#endif
           const int c8 = (i + lane) & (nvs / 2 - 1);                       // 8-wide k-chunk
           const float4 v0 = src[2 * c8], v1 = src[2 * c8 + 1];
           // scale by the power-of-two s_n, two elements per FMUL2 (exact)
@@ -1140,7 +1156,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
       }
       float lsse = 0.f;
 #pragma unroll 1
+#ifdef DVQ_KO_GATHER   // knock-out: no code gather, no z re-read, no z_q store
+      for (int part = 0; part < 0; ++part) {
+#else
       for (int part = 0; part < parts; ++part) {
+#endif
         const int c4 = (part << 5) | c4_lane;
         const char* ec = reinterpret_cast<const char*>(p.E + c4 * 4);
         const float* zp = p.z + (row0 + rbase) * D + c4 * 4;
