@@ -317,16 +317,19 @@ __global__ void __launch_bounds__(NT, 1) pointnet_trunk_tc_kernel(const TcTrunkP
 //
 // Tensor queue of round r (one issuing thread, in order):
 //     L1(r+2) 32 clk | L2(r+1) 320 clk | L3 chunk 0 (r) 512 clk | wait "chunk 1 drained" | L3 chunk 1 (r) 512 clk
-// Compute warps of round r, each step gated by the commit barrier of the MMA it consumes:
-//     max-epilogue of chunk 1 (r-1) -> arrive "chunk 1 drained";  layer-2 epilogue (r+1) -> h2[(r+1) & 1];
-//     layer-1 epilogue (r+2) -> h1;  coordinates of tile r+3 -> x16 (those of r+4 requested);  max-epilogue of chunk 0 (r).
+// Two groups of eight warps work underneath, each step gated by the commit barrier of the MMA it consumes:
+//     feed :  coordinates of tile r+3 -> x16 (those of r+4 requested);  layer-2 epilogue (r+1) -> h2[(r+1) & 1];
+//             layer-1 epilogue (r+2) -> h1
+//     drain:  max-epilogue of chunk 1 (r-1) -> arrive "chunk 1 drained";  max-epilogue of chunk 0 (r)
+// (as ONE group doing all five steps in sequence the round took 1.8x its tensor time: 869 TFLOP/s).
 // TMEM: layer-2 accumulator [0,128), layer-3 chunk 0 [128,256), chunk 1 [256,384), layer-1 accumulator [384,448).
 // The tile stream runs across the clouds of the CTA's group without draining the pipeline; running maxima are
 // written when a cloud ends.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int PT2 = 128;
-constexpr int CG2 = 2;                            // column groups: compute warps per TMEM lane quarter (4 measured 3 % slower than 2)
-constexpr int NC2 = CG2 * 128;
+constexpr int CG2 = 2;                            // column groups: warps of a role per TMEM lane quarter
+constexpr int NF2 = CG2 * 128;                    // feed warps (epilogues of layers 1 / 2, coordinates) ...
+constexpr int NC2 = 2 * NF2;                      // ... + as many drain warps (max-epilogues of layer 3): the two chains run side by side
 constexpr int NT2 = NC2 + 32;
 constexpr uint32_t H1B = KC1 * PT2 * 16;          // 20 KB
 constexpr uint32_t H2B = KC2 * PT2 * 16;          // 32 KB
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(NT2, 1) pointnet_trunk_tc2_kernel(const TcTrun
     tc::mbar_init(&bar_l2, 1);
     tc::mbar_init(&bar_l3[0], 1);
     tc::mbar_init(&bar_l3[1], 1);
-    tc::mbar_init(&bar_c1free, NC2 / 32);   // one arrival per compute warp
+    tc::mbar_init(&bar_c1free, NF2 / 32);   // one arrival per drain warp
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
@@ -476,7 +479,8 @@ __global__ void __launch_bounds__(NT2, 1) pointnet_trunk_tc2_kernel(const TcTrun
     }
   };
   // column group of this warp: the compute warps of a TMEM lane quarter split the accumulator columns evenly
-  const int cg = warp >> 2;
+  const bool feed = warp < NF2 / 32, drain = compute && !feed;
+  const int cg = (warp >> 2) & (CG2 - 1);
   const int prow = (warp & 3) * 32 + lane;   // tile point (layer 1 / 2 epilogues) or chunk channel (layer 3) = TMEM lane
   // `NCOL` accumulator columns starting at `col` -> ReLU -> FP16 pairs -> k-chunks kc0.. of row `prow` of an operand image
   auto drain_relu = [&](uint32_t col, uint8_t* img, int kc0, auto ncol_tag) {
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(NT2, 1) pointnet_trunk_tc2_kernel(const TcTrun
         }
       }
     }
-    if (compute) {
+    if (drain) {
       // (i) max-epilogue of chunk 1 of tile r-1 (its MMAs were the last of the previous round)
       if (r >= 1) {
         const int s = r - 1;
@@ -580,7 +584,7 @@ __global__ void __launch_bounds__(NT2, 1) pointnet_trunk_tc2_kernel(const TcTrun
         if (ok && cloud_done) {
           // the cloud of tile s is complete: combine the column groups, write this quarter's 256 maxima
           if (cg > 0) { mxs[(cg - 1) * 256 + prow] = run0; mxs[(cg - 1) * 256 + 128 + prow] = run1; }
-          asm volatile("bar.sync 2, %0;" ::"n"(NC2) : "memory");
+          asm volatile("bar.sync 2, %0;" ::"n"(NF2) : "memory");
           if (cg == 0) {
             float m0 = run0, m1 = run1;
 #pragma unroll
@@ -589,30 +593,33 @@ __global__ void __launch_bounds__(NT2, 1) pointnet_trunk_tc2_kernel(const TcTrun
             out[prow] = m0;
             out[128 + prow] = m1;
           }
-          asm volatile("bar.sync 2, %0;" ::"n"(NC2) : "memory");
+          asm volatile("bar.sync 2, %0;" ::"n"(NF2) : "memory");
           run0 = -INFINITY; run1 = -INFINITY;
         }
       }
-      // (ii) layer-2 epilogue of tile r+1 -> h2[(r+1)&1]
-      if (ok && r + 1 >= 0 && r + 1 < S) {
-        if (!tc::mbar_wait(&bar_l2, (uint32_t)((r + 1) & 1), errw, 1)) { ok = false; }
-        tc::tc_fence_after();
-        if (ok) l2_epilogue(r + 1);
-      }
-      // (iii) layer-1 epilogue of tile r+2 -> h1 (free: the layer-2 MMAs of tile r+1 completed above)
-      if (ok && r + 2 < S) {
-        if (!tc::mbar_wait(&bar_l1, (uint32_t)((r + 2) & 1), errw, 4)) { ok = false; }
-        tc::tc_fence_after();
-        if (ok) l1_epilogue();
-        // (iv) coordinates of tile r+3 -> x16 (free: the layer-1 MMA of tile r+2 completed above)
-        if (ok && r + 3 < S) { write_x16(); if (r + 4 < S) load_point(); }
-      }
-      // (v) max-epilogue of chunk 0 of tile r
+      // (ii) max-epilogue of chunk 0 of tile r
       if (ok && r >= 0 && r < S) {
         if (!tc::mbar_wait(&bar_l3[0], (uint32_t)(r & 1), errw, 2)) { ok = false; }
         tc::tc_fence_after();
         if (ok) run0 = fmaxf(run0, chunk_max(TM_C0));
       }
+    }
+    if (feed) {
+      // (a) coordinates of tile r+3 -> x16 (free once the layer-1 MMA of tile r+2, first in this round's queue, completed);
+      //     runs while the layer-2 MMAs of tile r+1 execute
+      if (r + 2 < S) {
+        if (!tc::mbar_wait(&bar_l1, (uint32_t)((r + 2) & 1), errw, 4)) { ok = false; }
+        tc::tc_fence_after();
+        if (ok && r + 3 < S) { write_x16(); if (r + 4 < S) load_point(); }
+      }
+      // (b) layer-2 epilogue of tile r+1 -> h2[(r+1)&1]
+      if (ok && r + 1 >= 0 && r + 1 < S) {
+        if (!tc::mbar_wait(&bar_l2, (uint32_t)((r + 1) & 1), errw, 1)) { ok = false; }
+        tc::tc_fence_after();
+        if (ok) l2_epilogue(r + 1);
+      }
+      // (c) layer-1 epilogue of tile r+2 -> h1 (free: the layer-2 MMAs of tile r+1 completed above)
+      if (ok && r + 2 < S) l1_epilogue();
     }
     tc::tc_fence_before();
     tc::fence_proxy_async_smem();
