@@ -205,8 +205,9 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
   const bool aligned16 = (reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(E) | reinterpret_cast<uintptr_t>(z_q)) % 16 == 0;
   const bool use_tc = tc_ok && path != DVQ_PATH_SIMT && (aligned16 || path == DVQ_PATH_TC);
 
+  const bool cached = (flags & DVQ_CODEBOOK_CACHED) != 0;   // the caller vouches for ee / CbMeta / operand image in the workspace
   profile_mark(0, true, s);
-  rc = launch_code_norms(E, K, D, ee, s);
+  if (!cached) rc = launch_code_norms(E, K, D, ee, s);
   profile_mark(0, false, s);
   if (rc) return rc;
   if (N > 0) {
@@ -217,7 +218,7 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
       profile_mark(1, true, s);
       float* row_nsq = vq_tc_rownorm_bytes(N, D) ? reinterpret_cast<float*>(ws + w.off_rowmeta) : nullptr;
       rc = launch_vq_tc(z, E, ee, N, K, D, train, z_q, idx, hist, sse, ws + w.off_bop, row_nsq, counters, row_list, cand_list,
-                        reinterpret_cast<int*>(ws + w.off_binned), (int)(vq_refine_binned_zero_bytes() / sizeof(int)), s);
+                        reinterpret_cast<int*>(ws + w.off_binned), (int)(vq_refine_binned_zero_bytes() / sizeof(int)), cached, s);
       profile_mark(1, false, s);
       if (rc) return rc;
       // exact FP32 refine of the rows the filter flagged (device-side count, no host sync): restricted to
@@ -571,7 +572,9 @@ int dvq_vq_forward_host(DvqHostCtx* c, const float* z_host, const float* E_host,
     DVQ_CUDA_CHECK(cudaEventRecord(c->ev_in[b], c->s_in));
     DVQ_CUDA_CHECK(cudaStreamWaitEvent(c->s_run, c->ev_in[b], 0));
     if (!(flags & DVQ_HOST_COPY_ONLY)) {
-      rc = dvq_vq_forward(c->z_dev[b], c->E_dev, rows, K, D, flags, c->zq_dev[b], c->idx_dev[b], nullptr, c->hist_dev,
+      // every full chunk after the first finds the codebook preparation of this call in the workspace (same E, rows, K, D)
+      const int cflags = flags | ((ci > 0 && rows == chunk) ? DVQ_CODEBOOK_CACHED : 0);
+      rc = dvq_vq_forward(c->z_dev[b], c->E_dev, rows, K, D, cflags, c->zq_dev[b], c->idx_dev[b], nullptr, c->hist_dev,
                           c->sse_dev, c->ws, c->ws_bytes, c->s_run);
       if (rc) return rc;
     }

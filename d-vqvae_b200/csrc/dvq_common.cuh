@@ -65,7 +65,7 @@ size_t vq_tc_rownorm_bytes(int64_t N, int D);
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
                  float* z_q, int64_t* idx, unsigned long long* hist, double* sse,
                  void* bop, float* row_nsq, int* counters, int* row_list, int* cand_list, int* zero_ints, int zero_n,
-                 cudaStream_t s);
+                 bool codebook_cached, cudaStream_t s);
 
 // candidate-restricted exact refine (vq_refine.cu); cand_list[i] = bit mask of 32*2^gshift-code groups
 bool vq_refine_supported(int K, int D);

@@ -574,7 +574,9 @@ __global__ void __launch_bounds__(NT2, 1) pointnet_trunk_tc2_kernel(const TcTrun
         const int s = r - 1;
         if (!tc::mbar_wait(&bar_l3[1], (uint32_t)(s & 1), errw, 3)) { ok = false; }
         tc::tc_fence_after();
+#ifndef DVQ_PN_KO_DRAIN
         if (ok) run1 = fmaxf(run1, chunk_max(TM_C1));
+#endif
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bar_c1free);
@@ -601,7 +603,9 @@ __global__ void __launch_bounds__(NT2, 1) pointnet_trunk_tc2_kernel(const TcTrun
       if (ok && r >= 0 && r < S) {
         if (!tc::mbar_wait(&bar_l3[0], (uint32_t)(r & 1), errw, 2)) { ok = false; }
         tc::tc_fence_after();
+#ifndef DVQ_PN_KO_DRAIN
         if (ok) run0 = fmaxf(run0, chunk_max(TM_C0));
+#endif
       }
     }
     if (feed) {
@@ -610,16 +614,22 @@ __global__ void __launch_bounds__(NT2, 1) pointnet_trunk_tc2_kernel(const TcTrun
       if (r + 2 < S) {
         if (!tc::mbar_wait(&bar_l1, (uint32_t)((r + 2) & 1), errw, 4)) { ok = false; }
         tc::tc_fence_after();
+#ifndef DVQ_PN_KO_FEED
         if (ok && r + 3 < S) { write_x16(); if (r + 4 < S) load_point(); }
+#endif
       }
       // (b) layer-2 epilogue of tile r+1 -> h2[(r+1)&1]
       if (ok && r + 1 >= 0 && r + 1 < S) {
         if (!tc::mbar_wait(&bar_l2, (uint32_t)((r + 1) & 1), errw, 1)) { ok = false; }
         tc::tc_fence_after();
+#ifndef DVQ_PN_KO_FEED
         if (ok) l2_epilogue(r + 1);
+#endif
       }
       // (c) layer-1 epilogue of tile r+2 -> h1 (free: the layer-2 MMAs of tile r+1 completed above)
+#ifndef DVQ_PN_KO_FEED
       if (ok && r + 2 < S) l1_epilogue();
+#endif
     }
     tc::tc_fence_before();
     tc::fence_proxy_async_smem();

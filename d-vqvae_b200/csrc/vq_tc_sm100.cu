@@ -79,7 +79,7 @@ constexpr int META_SLOTS = 4;
 // 44 % fewer tensor-core k-steps and shared-memory operand reads)
 constexpr bool USE_ZL = false;
 
-enum ErrCode { ERR_STAGE_FULL = 1, ERR_STAGE_EMPTY, ERR_A_FULL, ERR_A_EMPTY, ERR_ACC_FULL, ERR_ACC_EMPTY, ERR_B_FULL, ERR_FIN, ERR_SIDX };
+enum ErrCode { ERR_STAGE_FULL = 1, ERR_STAGE_EMPTY, ERR_A_FULL, ERR_A_EMPTY, ERR_ACC_FULL, ERR_ACC_EMPTY, ERR_B_FULL, ERR_FIN, ERR_SIDX, ERR_NOT_PREPARED };
 
 struct CbMeta {          // written by the prep kernels, read by the main kernel
   float s_E;             // power-of-two codebook scale
@@ -88,7 +88,9 @@ struct CbMeta {          // written by the prep kernels, read by the main kernel
   float delta_max;       // >= max_k ||eh_k - (-2 s_E e_k)||   (exact FP16 rounding residual)
   int half_E;            // s_E = 2^(10 - half_E)
   int degenerate;        // 1: codebook all-zero / non-finite -> every row goes to the exact kernel
+  int magic;             // cb_magic(K, D) once the preparation of this shape is complete (checked when DVQ_CODEBOOK_CACHED reuses it)
 };
+__host__ __device__ inline int cb_magic(int K, int D) { return 0x44565100 ^ (K << 12) ^ D; }
 
 struct TcParams {
   const float* z;
@@ -189,7 +191,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
 // ------------------------------------------------------------------------------------------------
 // codebook preparation (tiny): scale, FP16 operand image, exact rounding residual
 // ------------------------------------------------------------------------------------------------
-__global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, CbMeta* __restrict__ cb, int* __restrict__ counters,
+__global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, int D, CbMeta* __restrict__ cb, int* __restrict__ counters,
                                    int* __restrict__ zero_ints, int zero_n) {
   __shared__ float red[32];
   for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_ints[i] = 0;   // bin tables of the binned refine
@@ -217,9 +219,16 @@ __global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, CbMeta* 
     c.b0 = __half2float(__float2half_ru(c.s_E * emax * (1.f + 1e-6f)));
     c.eh_norm_bound = 2.f * c.s_E * emax * (1.f + 1.f / 512.f);
     c.delta_max = 0.f;
+    c.magic = cb_magic(K, D);
     *cb = c;
     for (int i = 0; i < 64; ++i) counters[i] = 0;
   }
+}
+
+// per-call reset when the codebook preparation is reused (DVQ_CODEBOOK_CACHED)
+__global__ void tc_reset_kernel(int* __restrict__ counters, int* __restrict__ zero_ints, int zero_n) {
+  for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_ints[i] = 0;
+  if (threadIdx.x < 64) counters[threadIdx.x] = 0;
 }
 
 // byte offset of element (code k, column d) in the global operand image: one block per (256-code chunk,
@@ -861,6 +870,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
     if (ST) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ST_SIDE));
     const int r = (warp - CONV_WARP0) * 32 + lane;
     const CbMeta cb = *p.cb;
+    if (cb.magic != cb_magic(K, D)) {   // DVQ_CODEBOOK_CACHED without a preparation of this shape in the workspace: fail loudly
+      *err_out = ERR_NOT_PREPARED;
+      __threadfence_system();
+      __trap();
+    }
     STAT_DECL(3);
 #ifdef DVQ_TC_STATS
     const long long conv_t0 = clock64();
@@ -1285,7 +1299,7 @@ size_t vq_tc_rownorm_bytes(int64_t N, int D) { return D > DSLICE ? align_up(size
 
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,
                  int64_t* idx, unsigned long long* hist, double* sse, void* bop, float* row_nsq, int* counters, int* row_list,
-                 int* cand_list, int* zero_ints, int zero_n, cudaStream_t s) {
+                 int* cand_list, int* zero_ints, int zero_n, bool codebook_cached, cudaStream_t s) {
   DeviceProps dp;
   int rc = device_props(&dp);
   if (rc) return rc;
@@ -1294,12 +1308,20 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   CbMeta* cb = static_cast<CbMeta*>(bop);
   uint8_t* bimg = static_cast<uint8_t*>(bop) + align_up(sizeof(CbMeta), 256);
   const SmemLayout L = smem_layout(K, D);
-  tc_cb_stats_kernel<<<1, 256, 0, s>>>(ee, K, cb, counters, zero_ints, zero_n);
-  DVQ_CUDA_CHECK(cudaGetLastError());
-  DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, (size_t)((K + 255) / 256) * L.ns * L.bchunk_bytes, s));
-  tc_cb_image_kernel<<<(K * 32 + 255) / 256, 256, 0, s>>>(E, ee, K, D, cb, bimg);
-  DVQ_CUDA_CHECK(cudaGetLastError());
-  count_launch(2);
+  if (codebook_cached) {
+    // DVQ_CODEBOOK_CACHED: CbMeta and the operand image in `bop` are those of this codebook; only the per-call
+    // counters and bin tables are reset
+    tc_reset_kernel<<<1, 256, 0, s>>>(counters, zero_ints, zero_n);
+    DVQ_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  } else {
+    tc_cb_stats_kernel<<<1, 256, 0, s>>>(ee, K, D, cb, counters, zero_ints, zero_n);
+    DVQ_CUDA_CHECK(cudaGetLastError());
+    DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, (size_t)((K + 255) / 256) * L.ns * L.bchunk_bytes, s));
+    tc_cb_image_kernel<<<(K * 32 + 255) / 256, 256, 0, s>>>(E, ee, K, D, cb, bimg);
+    DVQ_CUDA_CHECK(cudaGetLastError());
+    count_launch(2);
+  }
   if (D > DSLICE) {
     if (!row_nsq) return fail(DVQ_ERR_WORKSPACE, "tcgen05 path with e_dim > 64 needs the row-norm workspace");
     tc_row_nsq_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, s>>>(z, N, D, row_nsq);

@@ -17,6 +17,8 @@ LIB_PATH = os.environ.get("DVQ_LIB") or os.path.join(_HERE, "libdvq_sm100.so")
 ABI_VERSION = 1
 DVQ_TRAIN = 0x1
 DVQ_WRITE_ONEHOT = 0x2
+DVQ_CODEBOOK_CACHED = 0x200
+DVQ_PATH_MASK = 0x30
 DVQ_PATH_AUTO = 0x00
 DVQ_PATH_SIMT = 0x10
 DVQ_PATH_TC = 0x20

@@ -126,6 +126,7 @@ class VectorQuantizer(nn.Module):
     def __getstate__(self):     # deepcopy / pickle: the workspace is a cache, a process group cannot be pickled
         d = self.__dict__.copy()
         d["_ws"] = None
+        d["_cb_key"] = None
         d["process_group"] = None
         d.pop("last_stats", None)
         return d
@@ -141,6 +142,24 @@ class VectorQuantizer(nn.Module):
         self.path = _cabi.DVQ_PATH_AUTO      # DVQ_PATH_SIMT / DVQ_PATH_TC force a kernel
         self.process_group = None            # set by dvq.dist.shard_module for the multi-GPU path
         self._ws = None
+        # The codebook preparation (code norms, FP16 operand image, scale / residual bounds: three small launches) lives
+        # in the workspace and is reused while the codebook is unchanged: same storage and tensor version, same N,
+        # same workspace.  In-place writes through `.data` do not bump the version — call invalidate_codebook_cache()
+        # after such an edit, or set cache_codebook = False.
+        self.cache_codebook = True
+        self._cb_key = None
+
+    def invalidate_codebook_cache(self):
+        """Forget the cached codebook preparation (needed after editing ``embedding.weight.data`` in place)."""
+        self._cb_key = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._cb_key = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._cb_key = None
+        return super()._apply(fn, *args, **kwargs)
 
     # ------------------------------------------------------------------ helpers
     def _check(self, z: torch.Tensor, weight: torch.Tensor):
@@ -169,6 +188,13 @@ class VectorQuantizer(nn.Module):
     def _launch(self, z, weight, flags, z_q, idx, onehot, stats):
         n = z.numel() // self.e_dim
         ws = self._workspace(n, flags, z.device)
+        # (the 16-byte alignment of z decides between the tcgen05 and the FP32 kernel under AUTO: part of the key, since
+        #  only the former builds the operand image)
+        key = (weight.data_ptr(), weight._version, ws.data_ptr(), n, flags & _cabi.DVQ_PATH_MASK, str(z.device),
+               z.data_ptr() % 16 == 0 and z_q.data_ptr() % 16 == 0)
+        if self.cache_codebook and key == self._cb_key:
+            flags |= _cabi.DVQ_CODEBOOK_CACHED
+        self._cb_key = None          # (stays None if the launch raises)
         hist_ptr = stats.data_ptr() if stats is not None else None
         sse_ptr = stats.data_ptr() + 8 * self.n_e if stats is not None else None
         with torch.cuda.device(z.device):
@@ -176,6 +202,7 @@ class VectorQuantizer(nn.Module):
                 z.data_ptr(), weight.data_ptr(), n, self.n_e, self.e_dim, flags,
                 z_q.data_ptr(), idx.data_ptr(), onehot.data_ptr() if onehot is not None else None,
                 hist_ptr, sse_ptr, ws.data_ptr(), ws.numel(), _stream_ptr(z.device)), "dvq_vq_forward")
+        self._cb_key = key
 
     def last_counters(self, n: int, flags: int | None = None):
         """(rows refined by the exact FP32 kernel, tcgen05 pipeline error code) of the last forward

@@ -53,6 +53,10 @@ typedef enum DvqStatus {
 #define DVQ_PATH_SIMT 0x10    /* force the all-FP32 CUDA-core kernel                            */
 #define DVQ_PATH_TC 0x20      /* force the tcgen05 kernel (error if the shape is unsupported)   */
 #define DVQ_PATH_MASK 0x30
+#define DVQ_CODEBOOK_CACHED 0x200 /* dvq_vq_forward: the caller vouches that `workspace` still holds the codebook
+                                   * preparation (code norms, FP16 operand image, scale / residual bounds) of a previous
+                                   * call with the SAME E contents, N, K, D, flags & DVQ_PATH_MASK and workspace — it is
+                                   * reused instead of rebuilt (three small launches fewer per call) */
 #define DVQ_HOST_COPY_ONLY 0x100 /* dvq_vq_forward_host only: run the chunk pipeline's H2D / D2H copies without the
                                     kernels (outputs are undefined) - the copy-only ceiling of the host-buffer path */
 

@@ -522,3 +522,55 @@ def test_backward_kernel_sharded_scale_and_ema_hooks():
     with torch.no_grad():
         m2(zt, True)
     assert int((m2.last_stats[100:110] > 0).sum()) == 10            # the re-seeded codes are latents now: each is used
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", [0x00, 0x10])
+def test_codebook_preparation_is_cached_and_invalidated(path):
+    """DVQ_CODEBOOK_CACHED: the second call with an unchanged codebook reuses the workspace's code norms / operand image
+    (bit-identical outputs); a version bump, a different N or invalidate_codebook_cache() rebuild them."""
+    import dvq
+    from dvq import _cabi
+    rs = np.random.RandomState(11)
+    K, D, N = 512, 64, 20000
+    E = ((rs.rand(K, D) * 2 - 1) / K).astype(np.float32)
+    z = torch.from_numpy(rs.randn(N, D).astype(np.float32)).cuda()
+    m = _module(E, 1.0, 0.25, path)
+    m.onehot_limit_bytes = 0
+    seen = []
+    real = _cabi.lib.dvq_vq_forward
+
+    def spy(*a):
+        seen.append(int(a[5]) & _cabi.DVQ_CODEBOOK_CACHED)
+        return real(*a)
+
+    _cabi.lib.dvq_vq_forward = spy
+    try:
+        with torch.no_grad():
+            a = m(z, True)
+            b = m(z, True)                                  # cached
+            assert seen == [0, _cabi.DVQ_CODEBOOK_CACHED]
+            for x, y in zip(a, b):
+                if isinstance(x, torch.Tensor):
+                    assert torch.equal(x, y)
+            i_inf, _ = m(z, False)                          # inference flags, same codebook and N: still cached
+            assert seen[-1] == _cabi.DVQ_CODEBOOK_CACHED and torch.equal(i_inf, a[4])
+            m(z[:1000].contiguous(), True)                  # another N -> another workspace layout: rebuilt
+            assert seen[-1] == 0
+            m.embedding.weight.mul_(-1.0)                   # version bump: rebuilt, and the result follows the new codebook
+            c = m(z, True)
+            assert seen[-1] == 0
+            fresh = _module(-E, 1.0, 0.25, path)
+            fresh.onehot_limit_bytes = 0
+            d = fresh(z, True)
+            assert torch.equal(c[4], d[4]) and torch.equal(c[1], d[1])
+            m.embedding.weight.data.mul_(-1.0)              # no version bump: the caller invalidates
+            m.invalidate_codebook_cache()
+            e = m(z, True)
+            assert seen[-1] == 0 and torch.equal(e[4], a[4]) and torch.equal(e[1], a[1])
+            m.cache_codebook = False
+            m(z, True)
+            assert seen[-1] == 0
+    finally:
+        _cabi.lib.dvq_vq_forward = real
+    assert m.last_counters(N)[1] == 0
