@@ -190,6 +190,21 @@ __device__ __forceinline__ void bulk_g2s_keep_a(uint32_t smem_dst, const void* g
                "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
 }
+// 2-D tiled TMA load (tensor map built by cuTensorMapEncodeTiled, passed as a __grid_constant__ kernel parameter):
+// the box at element coordinates (c0 = innermost, c1) lands densely in shared memory, out-of-bounds elements as zeros;
+// the mbarrier receives the full box byte count
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_keep_a(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t bar) {   // L2 evict_last
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

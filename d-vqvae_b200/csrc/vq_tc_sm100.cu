@@ -38,9 +38,11 @@
 // async proxy signals.  TMEM: 512 columns = 2 accumulator stages of 256, so the MMA of one 256-code
 // chunk overlaps the epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays
 // resident in shared memory for K <= 512 and is streamed per row tile above.
+#include <cuda.h>        // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
 #include <cuda_fp16.h>
 #include <cstddef>
 #include <cstdlib>
+#include <cstring>
 
 #include "dvq_common.cuh"
 #include "tc_prims.cuh"
@@ -93,6 +95,7 @@ struct CbMeta {          // written by the prep kernels, read by the main kernel
 __host__ __device__ inline int cb_magic(int K, int D) { return 0x44565100 ^ (K << 12) ^ D; }
 
 struct TcParams {
+  CUtensorMap ztile;      // z as a [N, D] tensor, box = (slice columns, 128 rows): the staged slices of e_dim > 64 (one TMA load each)
   const float* z;
   const float* E;
   const uint8_t* bimg;
@@ -577,7 +580,7 @@ __device__ __forceinline__ void filter_subchunk2(uint32_t (&va)[32], uint32_t (&
 // ST: variant for streamed codebooks (many accumulator chunks per tile): the converter and gather warps work once per
 // tile and can live with 64 registers, so the epilogue warps get 104 and filter two sub-chunks at a time.
 template <int DT, bool TRAIN, bool LIST, bool CE, bool ST>
-__global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constant__ TcParams p) {
   static_assert(!(CE && ST), "the converter warps cannot hold the two-sub-chunk filter in 64 registers");
   constexpr int EPQX = CE ? EPQ + 1 : EPQ;       // filter warps per TMEM lane quarter
   constexpr int NB_ACC_THREADS = nb_acc_threads(EPQX), NB_ACC_HLP_THREADS = nb_acc_hlp_threads(EPQX), NB_FIN_THREADS = nb_fin_threads(EPQX);
@@ -726,13 +729,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
               else tc::bulk_g2s_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
             }
           } else {
-            // one bulk copy per row segment (ds * 4 bytes), issued by all lanes
-            if (lane == 0) tc::mbar_arrive_expect_tx_a(BAR(B_STAGE_FULL, s), (uint32_t)rows * ds * 4);
-            __syncwarp();
-            for (int r = lane; r < rows; r += 32) {
-              const float* src = p.z + (row0 + r) * D + sl * ds;
-              if (TRAIN) tc::bulk_g2s_keep_a(smem0 + L.stage[s] + (uint32_t)r * ds * 4, src, (uint32_t)ds * 4, BAR(B_STAGE_FULL, s));
-              else tc::bulk_g2s_a(smem0 + L.stage[s] + (uint32_t)r * ds * 4, src, (uint32_t)ds * 4, BAR(B_STAGE_FULL, s));
+            // one 2-D TMA load per slice: box (ds columns, 128 rows) at (sl * ds, row0); rows past N arrive as zeros and
+            // the barrier counts the whole box.  (As one bulk copy per 128- / 256-byte row segment — 128 per slice — this
+            // was the bound of the sliced shapes: 2.1x the filter time at K = 512, e_dim 512.)
+            if (lane == 0) {
+              tc::mbar_arrive_expect_tx_a(BAR(B_STAGE_FULL, s), (uint32_t)TM * ds * 4);
+              if (TRAIN) tc::tma_load_2d_keep_a(smem0 + L.stage[s], &p.ztile, sl * ds, (int)row0, BAR(B_STAGE_FULL, s));
+              else tc::tma_load_2d_a(smem0 + L.stage[s], &p.ztile, sl * ds, (int)row0, BAR(B_STAGE_FULL, s));
             }
           }
           __syncwarp();
@@ -1268,6 +1271,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const TcParams p) {
 
 }  // namespace
 
+// z [N, D] fp32 row-major as a 2-D tensor map with box (ds columns, TM rows), no swizzle: a slice of a row tile lands as
+// [row][ds floats], the layout the converter warps read
+static int encode_ztile(CUtensorMap* map, const float* z, int64_t N, int D, int ds) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DVQ_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(DVQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)N};
+  const cuuint64_t strides[1] = {(cuuint64_t)D * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)ds, (cuuint32_t)TM};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(z), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DVQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for z [%lld, %d]", (int)r, (long long)N, D);
+  return DVQ_OK;
+}
+
 bool vq_tc_supported(int64_t N, int K, int D) {
   if (N <= 0 || N > 2147483647LL - 256) return false;
   if (D < 16 || D > 512 || (D & (D - 1)) != 0) return false;   // power of two: index math is masks/shifts
@@ -1330,6 +1356,11 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   }
 
   TcParams p;
+  memset(&p.ztile, 0, sizeof(p.ztile));
+  if (D > DSLICE) {
+    rc = encode_ztile(&p.ztile, z, N, D, (int)L.ds);
+    if (rc) return rc;
+  }
   p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.row_nsq = row_nsq; p.N = N; p.K = K; p.D = D; p.train = train;
   p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list; p.cand_list = cand_list; p.cand_gshift = vq_tc_cand_gshift(K);
   p.stats = reinterpret_cast<unsigned long long*>(counters + 8);
