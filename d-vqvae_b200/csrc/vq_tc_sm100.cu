@@ -110,6 +110,7 @@ struct TcParams {
   int* counters;   // [0] refine-list length, [1] protocol error code
   int* row_list;
   int* cand_list;       // candidates of each listed row: group mask (bit g = codes [32*g<<gshift, ...)) or sub-chunk list
+  int layout_ovr;       // smem_layout override (0 = automatic)
   int cand_gshift;      // 0: mask mode (bit g = sub-chunk g); -1: list mode (see cand_union)
   unsigned long long* stats;   // optional wait-time accounting (DVQ_TC_STATS builds)
   int64_t ntiles;
@@ -145,7 +146,9 @@ __host__ __device__ inline uint32_t smem_place(SmemLayout& L, int K) {
   return off;
 }
 
-__host__ __device__ inline SmemLayout smem_layout(int K, int D) {
+// `ovr` != 0 forces (A images, z staging slots, ring slots) = (ovr / 100, ovr / 10 % 10, ovr % 10) for a streamed image
+// (experiments: DVQ_TC_LAYOUT; the launch passes it to the kernel so that both sides agree)
+__host__ __device__ inline SmemLayout smem_layout(int K, int D, int ovr = 0) {
   SmemLayout L;
   L.ds = (uint32_t)slice_width(D);
   L.ns = (uint32_t)D / L.ds;
@@ -173,6 +176,18 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D) {
   // tile on the third slot comes first; from 8 chunks on it only replaces the second z staging slot (a tile lasts
   // long enough for one); below that the layout of the resident case is kept.
   L.hist_in_smem = 0u;
+  if (ovr) {
+    L.a_bufs = (uint32_t)(ovr / 100); L.nstage = (uint32_t)(ovr / 10 % 10); L.nslots = (uint32_t)(ovr % 10);
+    smem_place(L, K);
+    return L;
+  }
+  if (nchunks == 2 && L.ns == 2) {
+    // K <= 512 at e_dim 128: four blocks per tile.  Measured at N = 16.8 M: one A image, one staging slot and a ring of
+    // three 6.9 ms, the two-of-everything layout the general rule picks 8.0 ms (K = 1024 at e_dim 128, eight blocks:
+    // 8.9 vs 8.4 ms the other way round)
+    L.a_bufs = 1; L.nstage = 1; L.nslots = 3;
+    if (smem_place(L, K) <= SMEM_LIMIT) return L;
+  }
   uint32_t best_score = 0, best_a = 1, best_st = 1, best_sl = 2;
   for (uint32_t a = 2; a >= 1; --a)
     for (uint32_t st = 2; st >= 1; --st)
@@ -595,7 +610,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
 
   const int D = DT > 0 ? DT : p.D;
   const int K = p.K;
-  const SmemLayout L = smem_layout(K, D);
+  const SmemLayout L = smem_layout(K, D, p.layout_ovr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ns = DT > 0 ? (DT > DSLICE ? DT / DSLICE : 1) : (int)L.ns;   // e_dim slices
   const int ds = DT > 0 ? (DT > DSLICE ? DSLICE : DT) : (int)L.ds;        // columns per slice
@@ -1333,7 +1348,12 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
     return fail(DVQ_ERR_BAD_ALIGN, "tcgen05 path needs 16-byte aligned z / E / z_q");
   CbMeta* cb = static_cast<CbMeta*>(bop);
   uint8_t* bimg = static_cast<uint8_t*>(bop) + align_up(sizeof(CbMeta), 256);
-  const SmemLayout L = smem_layout(K, D);
+  static const char* lay_env = getenv("DVQ_TC_LAYOUT");   // experiment: "a st sl" digits, e.g. 123 = 1 A image, 2 staging slots, 3 ring slots
+  int ovr = lay_env ? atoi(lay_env) : 0;
+  if (ovr && (((K + 255) / 256) * (D / slice_width(D)) <= 2 || smem_layout(K, D, ovr).total > SMEM_LIMIT || ovr / 100 < 1 || ovr / 100 > 2 ||
+              ovr / 10 % 10 < 1 || ovr / 10 % 10 > 2 || ovr % 10 < 2 || ovr % 10 > MAX_BSLOTS))
+    ovr = 0;   // resident images keep their layout; impossible requests are ignored
+  const SmemLayout L = smem_layout(K, D, ovr);
   if (codebook_cached) {
     // DVQ_CODEBOOK_CACHED: CbMeta and the operand image in `bop` are those of this codebook; only the per-call
     // counters and bin tables are reset
@@ -1363,6 +1383,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   }
   p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.row_nsq = row_nsq; p.N = N; p.K = K; p.D = D; p.train = train;
   p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list; p.cand_list = cand_list; p.cand_gshift = vq_tc_cand_gshift(K);
+  p.layout_ovr = ovr;
   p.stats = reinterpret_cast<unsigned long long*>(counters + 8);
   p.ntiles = (N + TM - 1) / TM;
   const size_t smem = L.total + 128;
