@@ -41,7 +41,8 @@ zD = 0
 for K, D in sorted(shapes, key=lambda s: (s[1], s[0])):
     g = torch.Generator(device=dev).manual_seed(4000 + K + D + 7919 * rank)
     cg = torch.Generator(device=dev).manual_seed(4000 + K + D)
-    if zD != D:
+    fresh = zD != D
+    if fresh:
         del z
         torch.cuda.empty_cache()
         z = torch.randn(N, D, device=dev, generator=g); zD = D
@@ -51,7 +52,7 @@ for K, D in sorted(shapes, key=lambda s: (s[1], s[0])):
     if world > 1:
         dvq.dist.shard_module(m)
     with torch.no_grad():
-        for _ in range(3 if (world > 1 and not out) else 1):   # the first shape also warms NCCL's channels up
+        for _ in range(3 if fresh else 1):   # the first shape of a row width also fills the caching allocator (and warms NCCL's channels up)
             m(z, True)
         torch.cuda.synchronize(dev)
         if world > 1:
