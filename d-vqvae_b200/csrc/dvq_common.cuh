@@ -104,6 +104,10 @@ int launch_pcnn_embed(const int64_t* x, int x_stride, int W, int B, int Bp, cons
                       float* img32, cudaStream_t s);
 int launch_pcnn_rows_to_image(const int64_t* label, int B, int Bp, const float* table, int n_rows, int kd, void* img16, cudaStream_t s);
 
+// MANO hand layer (mano_sm100.cu)
+int launch_mano(const DvqManoModel* m, const float* betas, const float* global_orient, const float* hand_pose, const float* transl, int B,
+                float* vertices, float* joints, cudaStream_t s);
+
 // PointNet
 size_t pointnet_workspace_bytes(int B, int C, int P, int flags);
 int launch_pointnet(const float* x, const DvqPointNetWeights* w, int B, int C, int P, int flags, float* feat,

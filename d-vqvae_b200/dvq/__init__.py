@@ -5,8 +5,9 @@ from . import _cabi  # noqa: F401  (fails loudly when the CUDA library is missin
 from . import dist  # noqa: F401
 from .grasp import GraspGenerator  # noqa: F401
 from .host import HostQuantizer  # noqa: F401
+from .mano import ManoLayer  # noqa: F401
 from .pointnet import PointNetEncoder, STN3d  # noqa: F401
 from .quantizer import LazyOneHot, VectorQuantizer  # noqa: F401
 from .vqvae import VQVAE  # noqa: F401
 
-__all__ = ["VectorQuantizer", "VQVAE", "PointNetEncoder", "STN3d", "LazyOneHot", "HostQuantizer", "GraspGenerator", "dist"]
+__all__ = ["VectorQuantizer", "VQVAE", "PointNetEncoder", "STN3d", "LazyOneHot", "HostQuantizer", "GraspGenerator", "ManoLayer", "dist"]

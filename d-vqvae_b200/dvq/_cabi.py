@@ -59,7 +59,14 @@ SYMBOLS = {
     "dvq_pointnet_workspace_bytes_ex": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
     "dvq_pointnet_forward_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "dvq_allreduce_stats": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "dvq_mano_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
 }
+
+
+class ManoModel(C.Structure):
+    """Mirror of ``DvqManoModel`` (include/dvq.h): device pointers to the fp32 tables of a MANO hand model."""
+    _fields_ = [(n, C.c_void_p) for n in ("v_template", "shapedirs", "posedirs", "j_regressor", "weights", "hands_components",
+                                          "pose_mean", "parents")] + [("ncomps", C.c_int)]
 
 
 class PointNetWeights(C.Structure):

@@ -9,8 +9,9 @@ Two things are pluggable because they are outside the hot path:
   (gen_net.py:92-100); the default draws uniform codes (random-init benchmarks; the reference's own
   random-init PixelCNN emits out-of-range codes).  ``pixelcnn_prior(model)`` adapts a reference
   ``GatedPixelCNN`` instance.
-* ``hand_layer(betas [B,10], pose [B,45]) -> vertices [B,778,3]`` — the reference uses the third-party
-  MANO layer (gen_net.py:117-118); the default is a fixed linear stub (no MANO assets in this image).
+* ``hand_layer(betas=[B,10], hand_pose=[B,45]) -> vertices [B,778,3]`` (or an object with ``.vertices``) — the reference
+  uses the third-party MANO layer (gen_net.py:117-118): pass ``dvq.ManoLayer.from_pkl('models/mano/MANO_RIGHT.pkl')`` for the
+  same arithmetic as one CUDA kernel; the default is a fixed linear stub (benchmarks without the MANO asset).
 """
 from __future__ import annotations
 
@@ -49,8 +50,8 @@ class LinearHandStub(nn.Module):
         self.register_buffer("template", 0.1 * torch.randn(778, 3, generator=g), persistent=False)
         self.register_buffer("basis", 0.01 * torch.randn(55, 778 * 3, generator=g), persistent=False)
 
-    def forward(self, betas, pose):
-        return self.template + (torch.cat([betas, pose], dim=1) @ self.basis).view(-1, 778, 3)
+    def forward(self, betas, hand_pose):
+        return self.template + (torch.cat([betas, hand_pose], dim=1) @ self.basis).view(-1, 778, 3)
 
 
 def uniform_prior(n_codes: int = 128, seed: int = 0):
@@ -135,7 +136,8 @@ class GraspGenerator(nn.Module):
         torch._assert_async(oob[0] == 0, "dvq.GraspGenerator: part-code index out of range")
         z_out[:, 6 * 256:] = feat_type
         recon = self.decoder(z_out).contiguous().view(B, 55)               # :109-113
-        verts = self.hand_layer(recon[:, :10], recon[:, 10:55])            # :117-118
+        verts = self.hand_layer(betas=recon[:, :10], hand_pose=recon[:, 10:55])   # :117-118 (global_orient = transl = 0)
+        verts = getattr(verts, "vertices", verts)                          # dvq.ManoLayer / mano / smplx return an output object
         hand_feat, _, _ = self.recon_encoder(verts.permute(0, 2, 1))       # :120
         recon_pos = self.pos_decoder(torch.cat([hand_feat, feat_pos], dim=1)).contiguous().view(B, 6)   # :121-123
         self.last = dict(feat_type=feat_type, feat_pos=feat_pos, idx6=idx6, obj_emb=obj_emb, codes=codes, verts=verts,

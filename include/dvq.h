@@ -185,6 +185,27 @@ DVQ_API int dvq_pcnn_embed(const int64_t* x, int x_stride, int W, int B, int Bp,
 DVQ_API int dvq_pcnn_rows_to_image(const int64_t* label, int B, int Bp, const float* table, int n_rows, int kd,
                                    void* img16, void* stream);
 
+/* ---- MANO hand layer — the third-party call at network/gen_net.py:116-118
+ *      self.rh_mano(betas=recon[:, :10], global_orient=0, hand_pose=recon[:, 10:55], transl=0).vertices
+ * (package `mano`, created at gen_diverse_grasp_obman.py:355-360: use_pca=True, num_pca_comps=45, flat_hand_mean=True).
+ * Linear blend skinning of MANO_{LEFT,RIGHT}.pkl (778 vertices, 16 joints, 10 shape and 45 pose dimensions); every
+ * table is a device pointer to fp32 data in the layout given here, 16-byte aligned. */
+typedef struct DvqManoModel {
+  const float* v_template;       /* [778*3]        vertex-major xyz                                              */
+  const float* shapedirs;        /* [10][778*3]    shape blend directions, one contiguous row per shape parameter */
+  const float* posedirs;         /* [135][778*3]   pose blend directions, one row per element of vec(R_1..15 - I) */
+  const float* j_regressor;      /* [16][778]                                                                     */
+  const float* weights;          /* [778][16]      skinning weights                                               */
+  const float* hands_components; /* [ncomps][45]   PCA basis rows (unused when ncomps == 0)                       */
+  const float* pose_mean;        /* [48]           added to [global_orient | hand pose]; zeros for flat_hand_mean */
+  const int* parents;            /* [16]           kinematic tree; joint 3f+1..3f+3 must form finger f's chain off joint 0 */
+  int ncomps;                    /* PCA components in hand_pose (0: hand_pose holds 45 axis-angle values)          */
+} DvqManoModel;
+/* betas [B,10], global_orient [B,3] or NULL (zeros), hand_pose [B, ncomps ? ncomps : 45], transl [B,3] or NULL
+ * -> vertices [B,778,3], joints [B,16,3] (posed joints; NULL to skip). */
+DVQ_API int dvq_mano_forward(const DvqManoModel* model, const float* betas, const float* global_orient, const float* hand_pose,
+                             const float* transl, int B, float* vertices, float* joints, void* stream);
+
 /* Host-buffer (end-to-end) form of the same forward: z_host/E_host/zq_host/idx_host are
  * HOST pointers (pinned for full overlap).  Rows are streamed through the GPU in chunks on
  * three internal streams (H2D, compute, D2H).  loss/perplexity are host floats (train only). */

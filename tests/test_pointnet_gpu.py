@@ -119,3 +119,18 @@ def test_pointnet_fp16_tc_vs_fp32_kernel_many_clouds():
     assert float((t16 - t32).abs().max()) <= TOL_TC * max(1.0, float(t32.abs().max()))
     f16b, _, _ = net(x[5:6].contiguous())
     assert torch.equal(f16b, f16[5:6])                     # clouds are independent, result is deterministic
+
+
+@pytest.mark.parametrize("scale,c", [(40.0, 4), (1e-3, 3), (1.0, 3)])
+def test_pointnet_fp16_tc_layer1_keeps_fp32_accuracy_over_coordinate_ranges(scale, c):
+    """Layer 1 runs on the tensor pipe with the coordinates and weights as hi/lo FP16 pairs (x.w + b to ~2^-22): large and tiny
+    coordinates (FP16 alone would lose them to its 11-bit mantissa / subnormal range) still agree with the FP32 kernel to the
+    same bar, for 3- and 4-channel clouds and more than one tile stream per CTA group."""
+    net = _encoder(33, c)
+    x = torch.from_numpy(po.make_cloud(34, 150, c, 700)).cuda() * scale
+    f32, t32, _ = net(x)
+    net.precision = "fp16_tc"
+    f16, t16, _ = net(x)
+    fs = float(f32.abs().max())
+    assert float((f16 - f32).abs().max()) <= TOL_TC * fs
+    assert float((t16 - t32).abs().max()) <= TOL_TC * max(1.0, float(t32.abs().max()))
