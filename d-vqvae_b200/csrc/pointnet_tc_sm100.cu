@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(NT, 1) pointnet_trunk_tc_kernel(const TcTrunkP
   const int q = blockIdx.x & 3;                       // channel quarter
   const int group = blockIdx.x >> 2, ngroups = gridDim.x >> 2;
   const int C = p.C, P = p.P;
-  float* xs = reinterpret_cast<float*>(smem + OFF_X);
   float4* w1s = reinterpret_cast<float4*>(smem + OFF_W1);
   float* b1s = reinterpret_cast<float*>(smem + OFF_W1 + 64 * 16);
   float* mxs = reinterpret_cast<float*>(smem + OFF_MAX);

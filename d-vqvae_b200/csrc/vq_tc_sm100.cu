@@ -1117,7 +1117,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
     if (ST) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ST_SIDE));
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_GATHER));
     const int gw = warp - GATHER_WARP0;
-    int* shist = reinterpret_cast<int*>(smem + L.hist);
     const int nv = D / 4;                              // float4 slots per row (power of two)
     const int rows_per_warp = TM / GATHER_WARPS;
     // lane -> (row, float4 column): a row is covered by lpr = min(nv, 32) lanes in `parts` = nv / lpr

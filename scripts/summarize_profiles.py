@@ -19,8 +19,8 @@ OUT = os.path.join(ROOT, "profiles")
 SRC = os.path.join(ROOT, "gpurun_out")
 
 
-def launches(tag):
-    path = os.path.join(SRC, "launches.csv")
+def launches(tag, csv_name="launches.csv", what="`bench.py --steps 2 --warmup 3`"):
+    path = os.path.join(SRC, csv_name)
     if not os.path.exists(path):
         return
     lines = [l for l in open(path) if not l.startswith("==")]
@@ -35,7 +35,7 @@ def launches(tag):
         agg.setdefault(r["Kernel Name"][:90], []).append(float(r["Metric Value"].replace(",", "")))
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(OUT, tag + "_launches.md"), "w") as f:
-        f.write("# %s — launch list of `bench.py --steps 2 --warmup 3` under ncu (gpu__time_duration.sum, --clock-control none)\n\n" % tag)
+        f.write("# %s — launch list of %s under ncu (gpu__time_duration.sum, --clock-control none)\n\n" % (tag, what))
         f.write("Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.\n\n| kernel | launches | total ns | share |\n|---|---|---|---|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write("| `%s` | %d | %.0f | %.3f |\n" % (k, len(v), sum(v), sum(v) / tot))
@@ -67,13 +67,16 @@ def full(tag, rep):
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[x[0]]
             return float(x[1].replace(",", "")) * scale
         if rd and wr:
+            # bench.py reads traffic_<tag>.json for the VQ filter kernel; other kernels get their own file
+            fname = "traffic_%s.json" % tag if name.startswith("vq_tc_kernel") else "traffic_%s_%s.json" % (tag, name)
             json.dump({"kernel": name, "dram_bytes_per_launch": tobytes(rd) + tobytes(wr), "read": tobytes(rd), "write": tobytes(wr),
-                       "source": os.path.basename(rep)}, open(os.path.join(OUT, "traffic_%s.json" % tag), "w"), indent=1)
+                       "source": os.path.basename(rep)}, open(os.path.join(OUT, fname), "w"), indent=1)
 
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     tag = sys.argv[1]
     launches(tag)
-    if len(sys.argv) > 2:
-        full(tag, sys.argv[2])
+    launches(tag + "_pointnet", "launches_pointnet.csv", "`scripts/bench_pointnet.py` (B = 4096, P = 3000)")
+    for rep in sys.argv[2:]:
+        full(tag, rep)
