@@ -157,7 +157,18 @@ vq_refine_kernel(const float* __restrict__ z, const float* __restrict__ E, const
       const int code_a = sa * 32 + lane, code_b = (sb < 0 ? sa : sb) * 32 + lane;
       const bool va = code_a < K, vb = sb >= 0 && code_b < K;
       float acc_a = 0.f, acc_b = 0.f;
-      if (SMEM_E) {
+      if (SMEM_E && sb < 0) {
+        // a single sub-chunk left (about half of the rows have an odd number of candidate sub-chunks): one FMA chain, half the
+        // shared-memory reads of the paired pass
+        const float* ea = es + (va ? code_a : 0) * PITCH;
+#pragma unroll
+        for (int d = 0; d < DT; d += 4) {
+          const float4 z4 = *reinterpret_cast<const float4*>(zb + d);   // broadcast read
+          const float4 a4 = *reinterpret_cast<const float4*>(ea + d);
+          acc_a = fmaf(z4.x, a4.x, acc_a); acc_a = fmaf(z4.y, a4.y, acc_a);
+          acc_a = fmaf(z4.z, a4.z, acc_a); acc_a = fmaf(z4.w, a4.w, acc_a);
+        }
+      } else if (SMEM_E) {
         const float* ea = es + (va ? code_a : 0) * PITCH;
         const float* eb = es + (vb ? code_b : 0) * PITCH;
 #pragma unroll
