@@ -260,21 +260,6 @@ __host__ __device__ inline size_t bimg_offset(int k, int d, int D) {
   return ((size_t)(k >> 8) * ns + sl) * block_bytes + (size_t)(dd >> 3) * (256 * 16) + (size_t)(k & 255) * 16 + (size_t)(dd & 7) * 2;
 }
 
-// ||z_n||^2 per row for e_dim > DSLICE (the converter needs the row scale before it sees the first slice)
-__global__ void tc_row_nsq_kernel(const float* __restrict__ z, int64_t N, int D, float* __restrict__ out) {
-  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= N) return;
-  const float4* src = reinterpret_cast<const float4*>(z + row * D);
-  float acc = 0.f;
-  for (int i = lane; i < D / 4; i += 32) {
-    const float4 v = __ldg(src + i);
-    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) out[row] = acc;
-}
-
 // one warp per code: eh = fp16(-2 s_E e), fold columns, residual norm -> atomic max
 __global__ void tc_cb_image_kernel(const float* __restrict__ E, const float* __restrict__ ee, int K, int D,
                                    CbMeta* __restrict__ cb, uint8_t* __restrict__ bimg) {
@@ -904,11 +889,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
       const int a = L.a_bufs == 2 ? (int)(it & 1) : 0;
       const uint32_t aph = L.a_bufs == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);   // phase of B_A_EMPTY[a] this tile waits past
       const int rows = (int)min((int64_t)TM, p.N - tile * TM);
-      // squared norm of the row: from the staged tile (single slice, lane-rotated conflict-free 128-bit reads)
-      // or from the pre-pass (sliced e_dim: the scale is needed before the first slice is converted)
+      // squared norm of the row from the staged slice (lane-rotated conflict-free 128-bit reads).  Single slice: the row's
+      // norm.  Sliced e_dim: the scale is needed before the first slice is converted, so it comes from an ESTIMATE — the
+      // first slice's norm times the number of slices — and the true norm is accumulated while the slices are converted
+      // (every bound below uses the true one; a row whose scaled norm then falls outside [2^8, 2^13] goes to the exact
+      // kernel).  FP16's relative precision does not depend on the scale, so the estimate costs no accuracy; it replaces a
+      // pre-pass kernel that read all of z once more.
       float nsq = 0.f;
       bool finite = true;
-      if (ns == 1) {
+      {
         const int s = L.nstage == 2 ? (int)(js & 1u) : 0;
         { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), L.nstage == 2 ? (js >> 1) & 1u : js & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
         if (warp == CONV_WARP0) TRACE(3, 0, 0);
@@ -930,9 +919,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
           float q0, q1, q2, q3;
           unpack_f32x2(n01, q0, q1); unpack_f32x2(n23, q2, q3);
           nsq = (q0 + q1) + (q2 + q3);
+          if (ns > 1) nsq *= (float)ns;
         }
-      } else if (r < rows) {
-        nsq = __ldg(p.row_nsq + tile * TM + r);
       }
       if (r < rows) finite = (nsq < 1e30f);   // false for inf / nan too
       // scales and bounds
@@ -943,15 +931,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
       const int rexp = cb.half_E - ex + 8;                              // fold scale r_n*2^8 = 2^rexp
       bool degenerate = (r < rows) && (tiny || !finite || cb.degenerate || rexp > 15 || rexp < -14);
       if (degenerate || r >= rows) s_n = 0.f;
-      const float zs = s_n * zn;                                        // scaled norm bound
-      const float f0a = __half2float(__float2half_ru(2.f * zs * (1.f + 1.f / 128.f)));
-      const float fr = (s_n == 0.f) ? 0.f : exp2f((float)rexp);
-      const float bias2 = 2.f * f0a * cb.b0;
-      float eps = zs * cb.delta_max * (1.f + 1.f / 64.f)
-                + bias2 * ((float)((USE_ZL ? 2 : 1) * ns * nk + 3) * (1.f / 1048576.f))   // tensor-core FP32 accumulation
-                + 16.f * fr * (1.f / 256.f);                                              // ee rounding (r_n = fr / 256)
-      if (USE_ZL) eps += (zs * (1.f / 4194304.f) + sqrtf((float)D) * (1.f / 33554432.f)) * cb.eh_norm_bound;   // zl rounding
       uint64_t rsq2 = pack_f32x2(0.f, 0.f);   // !USE_ZL: exact squared norm of the residual z' - zh that the product drops (even / odd partial sums)
+      uint64_t nacc2 = pack_f32x2(0.f, 0.f);  // sliced e_dim: squared norm of the scaled row z', accumulated slice by slice
       const uint64_t s_n2 = pack_f32x2(s_n, s_n);
       if (warp == CONV_WARP0) TRACE(3, 1, 0);
       { STAT_T0(); wait_or_trap(BAR(B_A_EMPTY, a), aph ^ 1u, err_out, ERR_A_EMPTY); STAT_ADD(1); }
@@ -960,7 +941,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
       uint8_t* aimg = smem + L.a_img[a] + (r >> 3) * 128 + (r & 7) * 16;
       for (int sl = 0; sl < ns; ++sl, ++js) {
         const int s = L.nstage == 2 ? (int)(js & 1u) : 0;
-        if (ns > 1) { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), L.nstage == 2 ? (js >> 1) & 1u : js & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
+        if (sl > 0) { STAT_T0(); wait_or_trap(BAR(B_STAGE_FULL, s), L.nstage == 2 ? (js >> 1) & 1u : js & 1u, err_out, ERR_STAGE_FULL); STAT_ADD(0); }
         const float4* src = reinterpret_cast<const float4*>(smem + L.stage[s]) + (size_t)r * nvs;
         uint8_t* aslice = aimg + (size_t)(sl * (nvs / 2)) * A_CHUNK_BYTES;
 #ifdef DVQ_KO_CONV   // knock-out: skip the FP16 conversion of the tile (the A image keeps stale data)
@@ -973,6 +954,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
           // scale by the power-of-two s_n, two elements per FMUL2 (exact)
           const uint64_t xp[4] = {fmul2(pack_f32x2(v0.x, v0.y), s_n2), fmul2(pack_f32x2(v0.z, v0.w), s_n2),
                                   fmul2(pack_f32x2(v1.x, v1.y), s_n2), fmul2(pack_f32x2(v1.z, v1.w), s_n2)};
+          if (ns > 1) nacc2 = ffma2(xp[3], xp[3], ffma2(xp[2], xp[2], ffma2(xp[1], xp[1], ffma2(xp[0], xp[0], nacc2))));
           // hi = fp16(x); with USE_ZL the second term is stored NEGATED, nl = fp16(hi - x) (one FHADD each, no
           // unpack) and the MMA issuer sets the A-negate bit of the instruction descriptor for the zl.eh products
           __half2 hi[4], lo[4];
@@ -991,6 +973,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
         }
         warp_arrive(BAR(B_STAGE_EMPTY, s));       // staging slot may be refilled
       }
+      // scaled norm bound: s_n * ||z|| from the exact norm (single slice) or the accumulated one (sliced; checked against
+      // the window the fold columns and the indicator arithmetic were laid out for)
+      float zs = s_n * zn;
+      if (ns > 1) {
+        float a0, a1;
+        unpack_f32x2(nacc2, a0, a1);
+        const float zt = sqrtf(a0 + a1) * (1.f + 1e-4f);
+        if (s_n != 0.f && !(zt >= 256.f && zt <= 8192.f)) degenerate = true;   // (also inf / nan)
+        zs = (s_n == 0.f) ? 0.f : fminf(zt, 8192.f);
+      }
+      const float f0a = __half2float(__float2half_ru(2.f * zs * (1.f + 1.f / 128.f)));
+      const float fr = (s_n == 0.f) ? 0.f : exp2f((float)rexp);
+      const float bias2 = 2.f * f0a * cb.b0;
+      float eps = zs * cb.delta_max * (1.f + 1.f / 64.f)
+                + bias2 * ((float)((USE_ZL ? 2 : 1) * ns * nk + 3) * (1.f / 1048576.f))   // tensor-core FP32 accumulation
+                + 16.f * fr * (1.f / 256.f);                                              // ee rounding (r_n = fr / 256)
+      if (USE_ZL) eps += (zs * (1.f / 4194304.f) + sqrtf((float)D) * (1.f / 33554432.f)) * cb.eh_norm_bound;   // zl rounding
       if (!USE_ZL) {
         float rs0, rs1;
         unpack_f32x2(rsq2, rs0, rs1);
@@ -1335,7 +1334,7 @@ size_t vq_tc_operand_bytes(int K, int D) {
   return align_up(sizeof(CbMeta), 256) + align_up((size_t)((K + 255) / 256) * L.ns * L.bchunk_bytes, 256);
 }
 
-size_t vq_tc_rownorm_bytes(int64_t N, int D) { return D > DSLICE ? align_up(sizeof(float) * (size_t)N, 256) : 0; }
+size_t vq_tc_rownorm_bytes(int64_t, int) { return 0; }   // (no row-norm pre-pass any more)
 
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,
                  int64_t* idx, unsigned long long* hist, double* sse, void* bop, float* row_nsq, int* counters, int* row_list,
@@ -1367,12 +1366,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
     DVQ_CUDA_CHECK(cudaGetLastError());
     count_launch(2);
   }
-  if (D > DSLICE) {
-    if (!row_nsq) return fail(DVQ_ERR_WORKSPACE, "tcgen05 path with e_dim > 64 needs the row-norm workspace");
-    tc_row_nsq_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, s>>>(z, N, D, row_nsq);
-    DVQ_CUDA_CHECK(cudaGetLastError());
-    count_launch();
-  }
+  (void)row_nsq;   // (the ||z||^2 pre-pass of the sliced shapes is gone: the converter warps accumulate the norm themselves)
 
   TcParams p;
   memset(&p.ztile, 0, sizeof(p.ztile));

@@ -574,3 +574,33 @@ def test_codebook_preparation_is_cached_and_invalidated(path):
     finally:
         _cabi.lib.dvq_vq_forward = real
     assert m.last_counters(N)[1] == 0
+
+
+@pytest.mark.parametrize("K,D", [(512, 128), (1024, 256), (2048, 512)])
+def test_sliced_path_row_scale_estimate_is_rigorous(K, D):
+    """e_dim > 64: the converter picks the row's FP16 scale from the FIRST slice's norm (estimate = norm x slices) and accumulates
+    the true norm while converting.  Rows whose energy is spread unevenly over the slices — the estimate off by 0.1x .. 30x —
+    must still get the exact kernel's index: in range they are filtered with an off-nominal scale (every bound uses the true
+    norm), out of range they go to the exact kernel."""
+    from dvq import _cabi
+    N = 4000 + 13
+    E = vo.default_codebook(K, D, 41)
+    z = vo.normal_latents(N, D, 42)
+    w = D // (D // 64 if D <= 256 else D // 32)          # columns of the first slice
+    for i, f in enumerate((1e-4, 0.03, 0.1, 0.3, 3.0, 10.0, 30.0)):
+        z[i::16, :w] *= f                                 # first slice scaled against the rest
+    z[7::16, w:] = 0.0                                    # energy in the first slice only
+    z[8::16, :w] = 0.0                                    # none in the first slice
+    out = {}
+    for name, path in (("simt", _cabi.DVQ_PATH_SIMT), ("tc", _cabi.DVQ_PATH_TC)):
+        m = _module(E, 1.0, 0.25, path)
+        m.onehot_limit_bytes = 0
+        with torch.no_grad():
+            out[name] = m(torch.from_numpy(z).cuda(), True)
+        assert m.last_counters(N)[1] == 0
+    idx_t, idx_s = out["tc"][4].cpu().numpy(), out["simt"][4].cpu().numpy()
+    n_mis, n_bad, worst = vo.allowed_index_mismatch(z, E, idx_t, idx_s)
+    assert n_bad == 0, (n_mis, worst)
+    assert vo.allowed_index_mismatch(z, E, idx_t, vo.forward_infer(z, E)[0])[1] == 0
+    assert np.array_equal(out["tc"][1].cpu().numpy().view(np.uint32), vo.zq_train_from_idx(z, E, idx_t).view(np.uint32))
+    assert rel_err(out["tc"][0].item(), out["simt"][0].item()) < REL
