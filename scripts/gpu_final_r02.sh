@@ -15,7 +15,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_bench.log 2>&1
 tail -1 gpurun_out/ncu_bench.log | cut -c1-200
 echo "== ncu launches: PointNet encoder"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_pointnet.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'pointnet|stn_head|decode' -c 60 --csv --log-file gpurun_out/launches_pointnet.csv \
     python scripts/bench_pointnet.py > gpurun_out/ncu_pointnet_launches.log 2>&1
 echo "== ncu full: config-2 filter kernel"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_tc_kernel -s 2 -c 1 -f -o gpurun_out/prof_r02_tc \
