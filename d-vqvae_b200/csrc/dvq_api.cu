@@ -90,8 +90,6 @@ VqWorkspace vq_workspace_layout(int64_t N, int K, int D, int flags) {
   if (may_tc) off = align_up(off + 2 * align_up(sizeof(int) * (size_t)N, 256), 256);
   w.off_bop = off;
   if (may_tc) off = align_up(off + vq_tc_operand_bytes(K, D), 1024);
-  w.off_rowmeta = off;
-  if (may_tc) off = align_up(off + vq_tc_rownorm_bytes(N, D), 256);
   w.off_binned = off;
   if (may_tc) off = align_up(off + vq_refine_binned_bytes(N), 256);
   w.total = off;
@@ -216,8 +214,7 @@ int dvq_vq_forward(const float* z, const float* E, int64_t N, int K, int D, int 
       int* row_list = reinterpret_cast<int*>(ws + w.off_rowlist);
       int* cand_list = reinterpret_cast<int*>(ws + w.off_rowlist + align_up(sizeof(int) * (size_t)N, 256));
       profile_mark(1, true, s);
-      float* row_nsq = vq_tc_rownorm_bytes(N, D) ? reinterpret_cast<float*>(ws + w.off_rowmeta) : nullptr;
-      rc = launch_vq_tc(z, E, ee, N, K, D, train, z_q, idx, hist, sse, ws + w.off_bop, row_nsq, counters, row_list, cand_list,
+      rc = launch_vq_tc(z, E, ee, N, K, D, train, z_q, idx, hist, sse, ws + w.off_bop, counters, row_list, cand_list,
                         reinterpret_cast<int*>(ws + w.off_binned), (int)(vq_refine_binned_zero_bytes() / sizeof(int)), cached, s);
       profile_mark(1, false, s);
       if (rc) return rc;

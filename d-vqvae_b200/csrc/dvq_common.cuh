@@ -41,7 +41,6 @@ struct VqWorkspace {
   size_t off_counters;  // int   [8]            refine-list length, overflow flags
   size_t off_rowlist;   // int   [2][N]         rows the tensor-core filter could not decide + their candidate masks
   size_t off_bop;       // operand image of the codebook for the tcgen05 path
-  size_t off_rowmeta;   // float [N]            ||z_n||^2 for the sliced tcgen05 path (e_dim > 64), else empty
   size_t off_binned;    // bin tables + (row, sub-chunk) pair list of the binned refine (vq_refine_binned.cu)
   size_t total;
 };
@@ -61,10 +60,9 @@ int launch_vq_simt(const float* z, const float* E, const float* ee, int64_t N, i
 bool vq_tc_supported(int64_t N, int K, int D);
 void vq_tc_layout_info(int K, int D, int* out8);   // dvq_debug_tc_layout
 size_t vq_tc_operand_bytes(int K, int D);
-size_t vq_tc_rownorm_bytes(int64_t N, int D);
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
                  float* z_q, int64_t* idx, unsigned long long* hist, double* sse,
-                 void* bop, float* row_nsq, int* counters, int* row_list, int* cand_list, int* zero_ints, int zero_n,
+                 void* bop, int* counters, int* row_list, int* cand_list, int* zero_ints, int zero_n,
                  bool codebook_cached, cudaStream_t s);
 
 // candidate-restricted exact refine (vq_refine.cu); cand_list[i] = bit mask of 32*2^gshift-code groups

@@ -100,7 +100,6 @@ struct TcParams {
   const float* E;
   const uint8_t* bimg;
   const CbMeta* cb;
-  const float* row_nsq;   // ||z_n||^2 per row (pre-pass), only for e_dim > DSLICE
   int64_t N;
   int K, D, train;
   float* zq;
@@ -1334,10 +1333,8 @@ size_t vq_tc_operand_bytes(int K, int D) {
   return align_up(sizeof(CbMeta), 256) + align_up((size_t)((K + 255) / 256) * L.ns * L.bchunk_bytes, 256);
 }
 
-size_t vq_tc_rownorm_bytes(int64_t, int) { return 0; }   // (no row-norm pre-pass any more)
-
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train, float* z_q,
-                 int64_t* idx, unsigned long long* hist, double* sse, void* bop, float* row_nsq, int* counters, int* row_list,
+                 int64_t* idx, unsigned long long* hist, double* sse, void* bop, int* counters, int* row_list,
                  int* cand_list, int* zero_ints, int zero_n, bool codebook_cached, cudaStream_t s) {
   DeviceProps dp;
   int rc = device_props(&dp);
@@ -1366,7 +1363,6 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
     DVQ_CUDA_CHECK(cudaGetLastError());
     count_launch(2);
   }
-  (void)row_nsq;   // (the ||z||^2 pre-pass of the sliced shapes is gone: the converter warps accumulate the norm themselves)
 
   TcParams p;
   memset(&p.ztile, 0, sizeof(p.ztile));
@@ -1374,7 +1370,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
     rc = encode_ztile(&p.ztile, z, N, D, (int)L.ds);
     if (rc) return rc;
   }
-  p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.row_nsq = row_nsq; p.N = N; p.K = K; p.D = D; p.train = train;
+  p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.N = N; p.K = K; p.D = D; p.train = train;
   p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list; p.cand_list = cand_list; p.cand_gshift = vq_tc_cand_gshift(K);
   p.layout_ovr = ovr;
   p.stats = reinterpret_cast<unsigned long long*>(counters + 8);
