@@ -276,13 +276,13 @@ int dvq_vq_read_counters(const void* workspace, int64_t N, int K, int D, int fla
   const VqWorkspace w = vq_workspace_layout(N, K, D, flags);
   DVQ_CUDA_CHECK(cudaMemcpy(out4, static_cast<const char*>(workspace) + w.off_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost));
   if (getenv("DVQ_TC_STATS_PRINT")) {
-    unsigned long long st[14];
+    unsigned long long st[17];
     DVQ_CUDA_CHECK(cudaMemcpy(st, static_cast<const char*>(workspace) + w.off_counters + 32, sizeof(st), cudaMemcpyDeviceToHost));
-    static const char* names[14] = {"producer.wait_stage_empty", "mma.wait_a_full", "mma.wait_acc_empty", "mma.total",
+    static const char* names[17] = {"producer.wait_stage_empty", "mma.wait_a_full", "mma.wait_acc_empty", "mma.total",
                                     "conv.wait_stage_full", "conv.wait_a_empty", "conv.total", "epi0.wait_acc_full",
                                     "epi4.wait_fin_empty", "epi0.wait_fin_full", "epi0.wait_sidx_empty", "epi0.total",
-                                    "gather.wait_sidx_full", "gather.total"};
-    for (int i = 0; i < 14; ++i) fprintf(stderr, "[dvq tc stats] %-28s %14llu cycles (sum over CTAs)\n", names[i], st[i]);
+                                    "gather.wait_sidx_full", "gather.total", "mma.wait_b_full", "(unused)", "mma.wait_peer_acc_empty"};
+    for (int i = 0; i < 17; ++i) fprintf(stderr, "[dvq tc stats] %-28s %14llu cycles (sum over CTAs)\n", names[i], st[i]);
     if (N >= 65536) {   // pipeline timeline of CTA 3, tiles 8..11 (see TRACE in vq_tc_sm100.cu)
       static long long tr[5 * 8 * 8];
       DVQ_CUDA_CHECK(cudaMemcpy(tr, static_cast<const char*>(workspace) + w.off_rowlist + (size_t)(N - 8192) * sizeof(int), sizeof(tr),

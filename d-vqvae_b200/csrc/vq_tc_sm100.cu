@@ -81,7 +81,8 @@ constexpr int META_SLOTS = 4;
 // 44 % fewer tensor-core k-steps and shared-memory operand reads)
 constexpr bool USE_ZL = false;
 
-enum ErrCode { ERR_STAGE_FULL = 1, ERR_STAGE_EMPTY, ERR_A_FULL, ERR_A_EMPTY, ERR_ACC_FULL, ERR_ACC_EMPTY, ERR_B_FULL, ERR_FIN, ERR_SIDX, ERR_NOT_PREPARED };
+enum ErrCode { ERR_STAGE_FULL = 1, ERR_STAGE_EMPTY, ERR_A_FULL, ERR_A_EMPTY, ERR_ACC_FULL, ERR_ACC_EMPTY, ERR_B_FULL, ERR_FIN, ERR_SIDX, ERR_NOT_PREPARED,
+               ERR_PEER_A_FULL, ERR_PEER_ACC_EMPTY };
 
 struct CbMeta {          // written by the prep kernels, read by the main kernel
   float s_E;             // power-of-two codebook scale
@@ -92,10 +93,11 @@ struct CbMeta {          // written by the prep kernels, read by the main kernel
   int degenerate;        // 1: codebook all-zero / non-finite -> every row goes to the exact kernel
   int magic;             // cb_magic(K, D) once the preparation of this shape is complete (checked when DVQ_CODEBOOK_CACHED reuses it)
 };
-__host__ __device__ inline int cb_magic(int K, int D) { return 0x44565100 ^ (K << 12) ^ D; }
+__host__ __device__ inline int cb_magic(int K, int D, bool pair = false) { return (0x44565100 ^ (K << 12) ^ D) + (pair ? 0x40000000 : 0); }
 
 struct TcParams {
   CUtensorMap ztile;      // z as a [N, D] tensor, box = (slice columns, 128 rows): the staged slices of e_dim > 64 (one TMA load each)
+  CUtensorMap bmap[2];    // CTA-pair kernel: the operand image as [bytes / 1024, 256] int32, box = one half block without ([0]) / with ([1]) the fold columns
   const float* z;
   const float* E;
   const uint8_t* bimg;
@@ -115,7 +117,8 @@ struct TcParams {
   int64_t ntiles;
 };
 
-constexpr int MAX_BSLOTS = 4;           // ring slots of the streamed codebook image
+constexpr int MAX_BSLOTS = 8;           // ring slots of the streamed codebook image (barrier arrays)
+constexpr int MAX_BSLOTS_SOLO = 4;      // single-CTA kernel: largest ring the layout search considers (whole 256-code blocks)
 
 struct SmemLayout {
   uint32_t bimg, a_img[2], stage[2], meta, fin, sidx, hist, total;
@@ -123,6 +126,7 @@ struct SmemLayout {
   uint32_t bchunk_bytes, hist_in_smem;           // one ring slot: (256 codes) x (one e_dim slice + the fold columns)
   uint32_t ns, ds, a_bufs, bslice_bytes;         // e_dim = ns slices of ds columns; a slice without the fold columns
   uint32_t nslots, nstage;                       // ring slots (2..MAX_BSLOTS), z staging slots (1..2)
+  uint32_t bcodes;                               // codes per ring slot: 256, or 128 in the CTA-pair kernel (each CTA holds half a block)
 };
 
 constexpr uint32_t SMEM_LIMIT = 227u * 1024u - 640u;   // dynamic shared memory budget (alignment slack + static barriers)
@@ -147,17 +151,19 @@ __host__ __device__ inline uint32_t smem_place(SmemLayout& L, int K) {
 
 // `ovr` != 0 forces (A images, z staging slots, ring slots) = (ovr / 100, ovr / 10 % 10, ovr % 10) for a streamed image
 // (experiments: DVQ_TC_LAYOUT; the launch passes it to the kernel so that both sides agree)
-__host__ __device__ inline SmemLayout smem_layout(int K, int D, int ovr = 0) {
+// `pair`: layout of the CTA-pair kernel (cta_group::2) — always streamed, a ring slot holds this CTA's half (128 codes) of a block
+__host__ __device__ inline SmemLayout smem_layout(int K, int D, int ovr = 0, bool pair = false) {
   SmemLayout L;
   L.ds = (uint32_t)slice_width(D);
   L.ns = (uint32_t)D / L.ds;
+  L.bcodes = pair ? 128u : 256u;
   const uint32_t kc_s = L.ds / 8, kc_a = (uint32_t)((USE_ZL ? 2 : 1) * D + 16) / 8;
-  L.bslice_bytes = kc_s * 256u * 16u;
-  L.bchunk_bytes = (kc_s + 2u) * 256u * 16u;
+  L.bslice_bytes = kc_s * L.bcodes * 16u;
+  L.bchunk_bytes = (kc_s + 2u) * L.bcodes * 16u;
   L.a_bytes = kc_a * A_CHUNK_BYTES;
   L.stage_bytes = (uint32_t)TM * L.ds * 4;
   const uint32_t nchunks = (uint32_t)(K + 255) / 256;
-  if (nchunks * L.ns <= 2) {
+  if (!pair && nchunks * L.ns <= 2) {
     // resident operand image (two slots hold it for the life of the CTA).  Preference order when shared memory is
     // short: drop the shared-memory histogram (global atomics), then the second A image (the converters then
     // wait for the previous tile's MMAs)
@@ -180,7 +186,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D, int ovr = 0) {
     smem_place(L, K);
     return L;
   }
-  if (nchunks == 2 && L.ns == 2) {
+  if (!pair && nchunks == 2 && L.ns == 2) {
     // K <= 512 at e_dim 128: four blocks per tile.  Measured at N = 16.8 M: one A image, one staging slot and a ring of
     // three 6.9 ms, the two-of-everything layout the general rule picks 8.0 ms (K = 1024 at e_dim 128, eight blocks:
     // 8.9 vs 8.4 ms the other way round)
@@ -190,7 +196,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D, int ovr = 0) {
   uint32_t best_score = 0, best_a = 1, best_st = 1, best_sl = 2;
   for (uint32_t a = 2; a >= 1; --a)
     for (uint32_t st = 2; st >= 1; --st)
-      for (uint32_t sl = MAX_BSLOTS; sl >= 2; --sl) {
+      for (uint32_t sl = pair ? MAX_BSLOTS : MAX_BSLOTS_SOLO; sl >= 2; --sl) {
         L.a_bufs = a; L.nstage = st; L.nslots = sl;
         if (smem_place(L, K) > SMEM_LIMIT) continue;
         const uint32_t sl3 = sl < 3u ? sl : 3u;
@@ -209,7 +215,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D, int ovr = 0) {
 // codebook preparation (tiny): scale, FP16 operand image, exact rounding residual
 // ------------------------------------------------------------------------------------------------
 __global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, int D, CbMeta* __restrict__ cb, int* __restrict__ counters,
-                                   int* __restrict__ zero_ints, int zero_n) {
+                                   int* __restrict__ zero_ints, int zero_n, bool pair) {
   __shared__ float red[32];
   for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_ints[i] = 0;   // bin tables of the binned refine
   float m = 0.f;
@@ -236,7 +242,7 @@ __global__ void tc_cb_stats_kernel(const float* __restrict__ ee, int K, int D, C
     c.b0 = __half2float(__float2half_ru(c.s_E * emax * (1.f + 1e-6f)));
     c.eh_norm_bound = 2.f * c.s_E * emax * (1.f + 1.f / 512.f);
     c.delta_max = 0.f;
-    c.magic = cb_magic(K, D);
+    c.magic = cb_magic(K, D, pair);
     *cb = c;
     for (int i = 0; i < 64; ++i) counters[i] = 0;
   }
@@ -251,17 +257,26 @@ __global__ void tc_reset_kernel(int* __restrict__ counters, int* __restrict__ ze
 // byte offset of element (code k, column d) in the global operand image: one block per (256-code chunk,
 // e_dim slice), each block laid out [d' / 8][k % 256][d' % 8] halfs exactly as its shared-memory ring slot;
 // the 16 fold columns (d >= D) follow the last slice of a chunk inside the same block
-__host__ __device__ inline size_t bimg_offset(int k, int d, int D) {
+// CTA-pair image (`pair`): every block is stored as two half blocks [d' / 8][k' % nh][d' % 8] of 128-code capacity, the
+// first holding the lower half of the chunk's codes (nh = codes in the chunk / 2; CTA 0's B operand), the second the upper
+// half (CTA 1's) — the split cta_group::2 expects of an N-wide B operand.
+__host__ __device__ inline size_t bimg_offset(int k, int d, int D, int K = 0, bool pair = false) {
   const int ds = slice_width(D), ns = D / ds;
   const size_t block_bytes = (size_t)(ds / 8 + 2) * 256 * 16;
   const int sl = d < D ? d / ds : ns - 1;
   const int dd = d < D ? d - sl * ds : ds + (d - D);
+  if (pair) {
+    const int c = k >> 8, kk = k & 255;
+    const int nh = (K - c * 256 < 256 ? K - c * 256 : 256) / 2;
+    const int half = kk >= nh ? 1 : 0;
+    return (((size_t)c * ns + sl) * 2 + half) * (block_bytes / 2) + (size_t)(dd >> 3) * (128 * 16) + (size_t)(kk - half * nh) * 16 + (size_t)(dd & 7) * 2;
+  }
   return ((size_t)(k >> 8) * ns + sl) * block_bytes + (size_t)(dd >> 3) * (256 * 16) + (size_t)(k & 255) * 16 + (size_t)(dd & 7) * 2;
 }
 
 // one warp per code: eh = fp16(-2 s_E e), fold columns, residual norm -> atomic max
 __global__ void tc_cb_image_kernel(const float* __restrict__ E, const float* __restrict__ ee, int K, int D,
-                                   CbMeta* __restrict__ cb, uint8_t* __restrict__ bimg) {
+                                   CbMeta* __restrict__ cb, uint8_t* __restrict__ bimg, bool pair) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= K) return;
   const float sE = cb->s_E;
@@ -272,7 +287,7 @@ __global__ void tc_cb_image_kernel(const float* __restrict__ E, const float* __r
     const __half h = __float2half_rn(v);
     const float r = v - __half2float(h);       // exact
     res = fmaf(r, r, res);
-    *reinterpret_cast<__half*>(bimg + bimg_offset(warp, d, D)) = h;
+    *reinterpret_cast<__half*>(bimg + bimg_offset(warp, d, D, K, pair)) = h;
   }
   res = warp_sum(res);
   if (lane < 16) {   // fold k-chunks D/8 and D/8+1
@@ -286,7 +301,7 @@ __global__ void tc_cb_image_kernel(const float* __restrict__ E, const float* __r
     if (lane == 2) v = mid;
     if (lane == 3) v = lo;
     const int d = D + lane;
-    *reinterpret_cast<__half*>(bimg + bimg_offset(warp, d, D)) = __float2half_rn(v);
+    *reinterpret_cast<__half*>(bimg + bimg_offset(warp, d, D, K, pair)) = __float2half_rn(v);
   }
   if (lane == 0) atomicMax(reinterpret_cast<int*>(&cb->delta_max), __float_as_int(sqrtf(res) * (1.f + 1e-5f)));
 }
@@ -349,6 +364,30 @@ __device__ __forceinline__ void wait_or_trap(uint32_t bar, uint32_t parity, int*
   }
 }
 
+// The same wait with acquire semantics at cluster scope: the phase was completed by the peer CTA's remote arrive
+__device__ __forceinline__ void wait_or_trap_cluster(uint32_t bar, uint32_t parity, int* err_out, int code) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 n;\n\t"
+      "mov.b32 n, 0;\n\t"
+      "DVQ_CWAIT:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "@p bra DVQ_CDONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, %4;\n\t"
+      "@p bra DVQ_CWAIT;\n\t"
+      "DVQ_CDONE:\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(100000u), "r"(1u << 22)
+      : "memory");
+  if (!ok) {
+    *err_out = code;
+    __threadfence_system();
+    __trap();
+  }
+}
+
 // Optional wait-time accounting (build with DVQ_TC_STATS=1): cycles spent in each wait site,
 // summed over the lanes that wait, flushed to stats[site] at the end of the kernel.
 #ifdef DVQ_TC_STATS
@@ -371,7 +410,7 @@ __device__ __forceinline__ void wait_or_trap(uint32_t bar, uint32_t parity, int*
 #ifdef DVQ_TC_STATS
 #define TRACE(role, ev, c_)                                                                                         \
   do {                                                                                                              \
-    if (blockIdx.x == 3 && (threadIdx.x & 31) == 0 && it >= 8 && it < 12 && p.N >= 65536)                            \
+    if (blockIdx.x == (PAIR ? 2 : 3) && (threadIdx.x & 31) == 0 && it >= 8 && it < 12 && p.N >= 65536)                            \
       reinterpret_cast<long long*>(p.row_list + p.N - 8192)[((role) * 8 + (ev)) * 8 + (int)(it - 8) * 2 + (c_)] = clock64(); \
   } while (0)
 #else
@@ -386,7 +425,9 @@ __device__ __forceinline__ float half_minus_float(uint32_t h16, float a) {
 }
 
 // All barriers live in one shared struct so that a site addresses its barrier as base + immediate.
-enum BarId { B_STAGE_FULL = 0, B_STAGE_EMPTY = 2, B_ACC_FULL = 4, B_A_EMPTY = 6, B_B_FULL = 8, B_B_EMPTY = 8 + MAX_BSLOTS, NBARS = 8 + 2 * MAX_BSLOTS };
+// (B_PEER_*: CTA-pair kernel, used in the leader CTA only — the peer CTA's forwarder warp arrives on them remotely)
+enum BarId { B_STAGE_FULL = 0, B_STAGE_EMPTY = 2, B_ACC_FULL = 4, B_A_EMPTY = 6, B_B_FULL = 8, B_B_EMPTY = 8 + MAX_BSLOTS,
+             B_PEER_A_FULL = 8 + 2 * MAX_BSLOTS, B_PEER_ACC_EMPTY = 10 + 2 * MAX_BSLOTS, NBARS = 12 + 2 * MAX_BSLOTS };
 // named barrier ids (0 is __syncthreads).  The accumulator-full relay has one barrier per (stage, warp group):
 // the helper warps of a tile must not wait for the owner warps, which are still merging / writing the previous
 // tile when the helpers are ready for the next one.
@@ -578,9 +619,19 @@ __device__ __forceinline__ void filter_subchunk2(uint32_t (&va)[32], uint32_t (&
 // with four warps per quarter every warp takes exactly two of a chunk's eight sub-chunks instead of 3 / 3 / 2).
 // ST: variant for streamed codebooks (many accumulator chunks per tile): the converter and gather warps work once per
 // tile and can live with 64 registers, so the epilogue warps get 104 and filter two sub-chunks at a time.
-template <int DT, bool TRAIN, bool LIST, bool CE, bool ST>
+// PAIR: CTA-pair kernel for streamed codebooks (cluster of two CTAs = the two SMs of a TPC, cta_group::2).  A streamed
+// shape at M = 128 needs 64 bytes of operand image per tensor-pipe cycle and SM, 1.5x what the L2 delivers to 148 SMs
+// (profiles/README.md), so the tensor pipe idles a third of the time.  The pair runs ONE M = 256 MMA per k-step: each CTA
+// converts its own 128-row tile and streams only its HALF of every operand block (N / 2 codes), the accumulator of each
+// CTA's rows lands in its own TMEM, and filter / gather work as in the single-CTA kernel.  The leader's (rank 0) warp 1
+// issues; both CTAs' operand loads complete on the leader's ring barrier (cp.async.bulk.tensor with cta_group::2), the
+// peer's warp 1 forwards "A image full" once per tile (remote arrive, release / acquire at cluster scope), the peer's filter
+// warps announce a freed accumulator stage with one remote arrive each; completions are committed to both CTAs' barriers
+// (multicast).
+template <int DT, bool TRAIN, bool LIST, bool CE, bool ST, bool PAIR = false>
 __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constant__ TcParams p) {
   static_assert(!(CE && ST), "the converter warps cannot hold the two-sub-chunk filter in 64 registers");
+  static_assert(!PAIR || DT == 0, "the CTA-pair kernel is the generic streamed kernel");
   constexpr int EPQX = CE ? EPQ + 1 : EPQ;       // filter warps per TMEM lane quarter
   constexpr int NB_ACC_THREADS = nb_acc_threads(EPQX), NB_ACC_HLP_THREADS = nb_acc_hlp_threads(EPQX), NB_FIN_THREADS = nb_fin_threads(EPQX);
   extern __shared__ __align__(128) uint8_t smem[];
@@ -594,14 +645,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
 
   const int D = DT > 0 ? DT : p.D;
   const int K = p.K;
-  const SmemLayout L = smem_layout(K, D, p.layout_ovr);
+  const SmemLayout L = smem_layout(K, D, p.layout_ovr, PAIR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = PAIR ? tc::cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs), 1 = peer
   const int ns = DT > 0 ? (DT > DSLICE ? DT / DSLICE : 1) : (int)L.ns;   // e_dim slices
   const int ds = DT > 0 ? (DT > DSLICE ? DSLICE : DT) : (int)L.ds;        // columns per slice
   const int nk = ds / 16;                      // k-steps per slice
   const int nchunks = (K + 255) / 256;         // accumulator chunks per tile
-  const bool resident = nchunks * ns <= 2;     // whole operand image fits the two ring slots
-  const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const bool resident = !PAIR && nchunks * ns <= 2;     // whole operand image fits the two ring slots
+  // tile of iteration `it`: CTA b takes tiles b, b + grid, ...; a pair takes the tile pairs (2u, 2u + 1), u = cluster id,
+  // cluster id + clusters, ... — both CTAs of a pair run the same number of iterations (the odd tile past the end has no rows)
+  const int64_t pair_units = (p.ntiles + 1) / 2;
+  const int64_t my_tiles = PAIR ? (pair_units > (int64_t)(blockIdx.x >> 1) ? (pair_units - 1 - (blockIdx.x >> 1)) / (gridDim.x >> 1) + 1 : 0)
+                                : (p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0);
+  // (block and grid indices are read at the point of use: held in a register they are spill candidates)
+  auto tile_of = [&](int64_t it) -> int64_t {
+    return PAIR ? 2 * ((int64_t)(blockIdx.x >> 1) + it * (int64_t)(gridDim.x >> 1)) + (int64_t)crank : (int64_t)blockIdx.x + it * gridDim.x;
+  };
   const int64_t total_chunks = my_tiles * nchunks;
 
   if (tid == 0) {
@@ -615,15 +675,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
       tc::mbar_init(&ctl.bars[B_B_FULL + i], 1);
       tc::mbar_init(&ctl.bars[B_B_EMPTY + i], 1);
     }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&ctl.bars[B_PEER_A_FULL + i], 1);
+      tc::mbar_init(&ctl.bars[B_PEER_ACC_EMPTY + i], 4 * EPQX);   // one remote arrival per filter warp of the peer CTA
+    }
     tc::fence_barrier_init();
   }
   if (L.hist_in_smem) {
     int* shist = reinterpret_cast<int*>(smem + L.hist);
     for (int k = tid; k < K; k += NTHREADS) shist[k] = 0;
   }
-  if (warp == 1) tc::tmem_alloc(&ctl.tmem_slot, 512);
+  if (warp == 1) {
+    if (PAIR) tc::tmem_alloc_pair(&ctl.tmem_slot, 512);
+    else tc::tmem_alloc(&ctl.tmem_slot, 512);
+  }
   tc::tc_fence_before();
   __syncthreads();
+  if (PAIR) tc::cluster_sync_all();   // the peer's barriers exist before a commit or a remote arrive reaches them
   tc::tc_fence_after();
   const uint32_t tmem_base = ctl.tmem_slot;
 
@@ -677,7 +745,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
       tc::tc_fence_before();
       if (wq == 0 && r < 32) TRACE(1, 1, c & 1);
       if (wq == 1 && r < 32) TRACE(2, 1, c & 1);
-      if ((int64_t)q + 2 < total_chunks) nb_arrive(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS);
+      if ((int64_t)q + 2 < total_chunks) {
+        if (PAIR && crank != 0) {
+          // peer CTA of a pair: this warp's share of the stage is read (tcgen05.wait::ld above) — tell the leader's issuer
+          // directly, one relaxed remote arrive per warp (a release at cluster scope would stall the warp for a fence)
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive_remote_relaxed(tc::map_to_cta(BAR(B_PEER_ACC_EMPTY, t), 0));
+        } else {
+          nb_arrive(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS);
+        }
+      }
     }
     if (LIST && st.ncand > 3) st.cand = CAND_OVERFLOW;   // an entry was shifted out: the refine scans every code of this row
   };
@@ -713,9 +790,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
       uint32_t js = 0;   // running slice counter of the staging ring
       STAT_DECL(1);
       for (int64_t it = 0; it < my_tiles; ++it) {
-        const int64_t tile = blockIdx.x + it * gridDim.x;
+        const int64_t tile = tile_of(it);
         const int64_t row0 = tile * TM;
-        const int rows = (int)min((int64_t)TM, p.N - row0);
+        const int rows = (int)max((int64_t)0, min((int64_t)TM, p.N - row0));
         for (int sl = 0; sl < ns; ++sl, ++js) {
           const int s = L.nstage == 2 ? (int)(js & 1u) : 0;
           const uint32_t ph = L.nstage == 2 ? (js >> 1) & 1u : js & 1u;
@@ -723,9 +800,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
           if (ns == 1) {
             if (lane == 0) {   // the whole tile is one contiguous block
               const uint32_t bytes = (uint32_t)rows * D * 4;
-              tc::mbar_arrive_expect_tx_a(BAR(B_STAGE_FULL, s), bytes);
-              if (TRAIN) tc::bulk_g2s_keep_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
-              else tc::bulk_g2s_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
+              if (PAIR && rows == 0) tc::mbar_arrive_a(BAR(B_STAGE_FULL, s));   // the pair's tile past the end: nothing to load
+              else {
+                tc::mbar_arrive_expect_tx_a(BAR(B_STAGE_FULL, s), bytes);
+                if (TRAIN) tc::bulk_g2s_keep_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
+                else tc::bulk_g2s_a(smem0 + L.stage[s], p.z + row0 * D, bytes, BAR(B_STAGE_FULL, s));
+              }
             }
           } else {
             // one 2-D TMA load per slice: box (ds columns, 128 rows) at (sl * ds, row0); rows past N arrive as zeros and
@@ -746,11 +826,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
     // ===================== codebook streamer: (chunk, slice) blocks of the operand image from L2 -> ring of L.nslots slots =====================
     if (lane == 0 && !resident) {
       uint32_t slot = 0, ph = 0;   // ring position: slot index and the phase bit of its barriers
+      const uint32_t leader_bfull = PAIR ? tc::map_to_cta(BAR(B_B_FULL, 0), 0) : 0u;
       for (int64_t it = 0; it < my_tiles; ++it) {
         for (int c = 0; c < nchunks; ++c) {
           for (int sl = 0; sl < ns; ++sl) {
             wait_or_trap(BAR(B_B_EMPTY, slot), ph ^ 1u, err_out, ERR_B_FULL);
             const uint32_t bytes = sl == ns - 1 ? L.bchunk_bytes : L.bslice_bytes;   // the fold columns ride with the last slice
+            // (pair kernel: block (c, sl) is stored as two half blocks, this CTA streams its own)
+            if (PAIR) {
+              // block (c, sl) is stored as two half blocks; each CTA streams its own half into its own ring slot with one 2-D
+              // TMA load that completes on the LEADER's barrier (cta_group::2), which therefore counts both halves
+              if (crank == 0) tc::mbar_arrive_expect_tx_a(BAR(B_B_FULL, slot), 2u * bytes);
+              const int row = (int)(((size_t)((c * ns + sl) * 2 + (int)crank) * L.bchunk_bytes) >> 10);
+              tc::tma_load_2d_pair_a(smem0 + L.bimg + slot * L.bchunk_bytes, &p.bmap[sl == ns - 1 ? 1 : 0], 0, row, leader_bfull + 8u * slot);
+              if (++slot == L.nslots) { slot = 0; ph ^= 1u; }
+              continue;
+            }
             const uint8_t* src = p.bimg + (size_t)(c * ns + sl) * L.bchunk_bytes;
             tc::mbar_arrive_expect_tx_a(BAR(B_B_FULL, slot), bytes);
             for (uint32_t off = 0; off < bytes; off += 16384) {
@@ -770,9 +861,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
     // named barrier, so that only this warp ever polls.  The next chunk is issued after the relay: with
     // two TMEM stages and an epilogue that takes longer per chunk than the MMAs, the tensor pipe is
     // never the one waited for.
-    {
+    if (PAIR && crank != 0) {
+      // ---- peer CTA of a pair: forward "A image of this tile written" to the leader's mbarrier (the freed accumulator stages
+      // are announced by the filter warps themselves, the ring slots by the TMA loads)
+      const uint32_t peer_bars = tc::map_to_cta(bar0, 0);   // the leader's barrier struct (same offsets)
+#define PEER_BAR(id, i) (peer_bars + 8u * (uint32_t)((id) + (i)))
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        nb_sync(NB_A_FULL + (int)(it & 1), NB_A_THREADS);                     // converters: fence.proxy.async + bar.arrive
+        if (lane == 0) tc::mbar_arrive_remote(PEER_BAR(B_PEER_A_FULL, it & 1));
+      }
+#undef PEER_BAR
+    } else {
       if (resident) for (int b = 0; b < nchunks * ns; ++b) wait_or_trap(BAR(B_B_FULL, b), 0, err_out, ERR_B_FULL);
-      const uint32_t b_lbo = 256u * 16u, b_sbo = 128;
+      const uint32_t b_lbo = (PAIR ? 128u : 256u) * 16u, b_sbo = 128;
       const uint32_t a_lbo = A_CHUNK_BYTES, a_sbo = 128;
       // descriptors are (address >> 4) in the low bits: advancing by one k-step (two 8-wide k-chunks)
       // is a constant add that never carries out of the 14-bit address field
@@ -786,25 +887,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
       const uint32_t barbase = tc::smem_u32(ctl.bars);
       uint32_t q = 0;           // accumulator chunks consumed so far
       uint32_t rslot = 0, rph = 0;   // ring position of the next operand block (slot, phase bit)
-      STAT_DECL(3);
+      STAT_DECL(6);   // [3..5]: ring slot full (local), the peer's half, the peer's accumulator stage
 #ifdef DVQ_TC_STATS
       const long long mma_t0 = clock64();
 #endif
       for (int64_t it = 0; it < my_tiles; ++it) {
         const int a = L.a_bufs == 2 ? (int)(it & 1) : 0;
         { STAT_T0(); nb_sync(NB_A_FULL + (int)(it & 1), NB_A_THREADS); STAT_ADD(0); }
+        if (PAIR) wait_or_trap_cluster(BAR(B_PEER_A_FULL, it & 1), (uint32_t)((it >> 1) & 1), err_out, ERR_PEER_A_FULL);
         TRACE(0, 0, 0);
         for (int c = 0; c < nchunks; ++c, ++q) {
           const uint32_t t = q & 1u;
-          if (q >= 2) { STAT_T0(); nb_sync(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS); STAT_ADD(1); }
+          if (q >= 2) {
+            STAT_T0(); nb_sync(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS);
+            STAT_ADD(1);
+            if (PAIR) { STAT_T0(); wait_or_trap_cluster(BAR(B_PEER_ACC_EMPTY, t), ((q >> 1) & 1u) ^ 1u, err_out, ERR_PEER_ACC_EMPTY); STAT_ADD(5); }
+          }
           tc::tc_fence_after();
           TRACE(0, 1, c & 1);
           const int n = min(256, K - c * 256);
-          const uint32_t idesc = tc::make_idesc_f16(128, n, 0);
+          const uint32_t idesc = tc::make_idesc_f16(PAIR ? 256 : 128, n, 0);
           const uint32_t d_tmem = tmem_base + t * 256u;
           for (int sl = 0; sl < ns; ++sl) {
             const uint32_t bslot = resident ? (uint32_t)(c * ns + sl) : rslot;
-            if (!resident) wait_or_trap(BAR(B_B_FULL, bslot), rph, err_out, ERR_B_FULL);
+            if (PAIR) { STAT_T0(); wait_or_trap_cluster(BAR(B_B_FULL, bslot), rph, err_out, ERR_B_FULL); STAT_ADD(3); }   // both halves (the peer's TMA completes here too)
+            else if (!resident) { STAT_T0(); wait_or_trap(BAR(B_B_FULL, bslot), rph, err_out, ERR_B_FULL); STAT_ADD(3); }
             tc::tc_fence_after();
             if (tc::elect_one()) {
               const uint64_t bc = b_desc0 + (uint64_t)((bslot * L.bchunk_bytes) >> 4);
@@ -812,6 +919,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
               uint32_t acc = sl > 0 ? 1u : 0u;
 #pragma unroll
               for (int j = 0; j < nk; ++j) {   // zh . eh, one slice
+                if (PAIR) tc::umma_f16_pair(d_tmem, ad, bd, idesc, acc); else
                 tc::umma_f16(d_tmem, ad, bd, idesc, acc);
 #ifdef DVQ_KO_MMA2   // timing model of a half-rate MMA kind (kind::tf32 straight from the staged fp32 tile): every k-step twice
                 tc::umma_f16(d_tmem, ad, bd, idesc, 1);
@@ -826,12 +934,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
                   ad += a_step; bd += b_step;
                 }
               }
+              if (PAIR) {   // the same sequence on the pair; every completion goes to both CTAs' barriers
+                if (sl == ns - 1) {
+                  tc::umma_f16_pair(d_tmem, ad, bd, idesc, 1);
+                  tc::umma_commit_pair_a(barbase + 8u * (B_ACC_FULL + t));
+                  if (c == nchunks - 1) tc::umma_commit_pair_a(barbase + 8u * (uint32_t)(B_A_EMPTY + a));
+                }
+                tc::umma_commit_pair_a(barbase + 8u * (B_B_EMPTY + bslot));
+              } else {
               if (sl == ns - 1) {
                 tc::umma_f16(d_tmem, ad, bd, idesc, 1);   // fold columns: they follow the last slice in A and in the ring slot
                 tc::umma_commit_a(barbase + 8u * (B_ACC_FULL + t));
                 if (c == nchunks - 1) tc::umma_commit_a(barbase + 8u * (uint32_t)(B_A_EMPTY + a));  // every MMA of this tile done: A image free
               }
               if (!resident) tc::umma_commit_a(barbase + 8u * (B_B_EMPTY + bslot));   // ring slot free once these MMAs have read it
+              }
             }
             if (!resident && ++rslot == L.nslots) { rslot = 0; rph ^= 1u; }
             __syncwarp();
@@ -851,6 +968,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
       }
 #ifdef DVQ_TC_STATS
       stat_acc[2] = clock64() - mma_t0;
+      if ((threadIdx.x & 31) == 0) for (int i = 3; i < 6; ++i) atomicAdd(p.stats + 11 + i, (unsigned long long)stat_acc[i]);
 #endif
       STAT_FLUSH(3, 1);
     }
@@ -872,7 +990,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
     if (ST) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ST_SIDE));
     const int r = (warp - CONV_WARP0) * 32 + lane;
     const CbMeta cb = *p.cb;
-    if (cb.magic != cb_magic(K, D)) {   // DVQ_CODEBOOK_CACHED without a preparation of this shape in the workspace: fail loudly
+    if (cb.magic != cb_magic(K, D, PAIR)) {   // DVQ_CODEBOOK_CACHED without a preparation of this shape in the workspace: fail loudly
       *err_out = ERR_NOT_PREPARED;
       __threadfence_system();
       __trap();
@@ -884,10 +1002,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
     const int nvs = ds / 4;   // float4 per row of one slice
     uint32_t js = 0;          // running slice counter of the staging ring
     auto convert_tile = [&](int64_t it) {
-      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t tile = tile_of(it);
       const int a = L.a_bufs == 2 ? (int)(it & 1) : 0;
       const uint32_t aph = L.a_bufs == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);   // phase of B_A_EMPTY[a] this tile waits past
-      const int rows = (int)min((int64_t)TM, p.N - tile * TM);
+      const int rows = (int)max((int64_t)0, min((int64_t)TM, p.N - tile * TM));
       // squared norm of the row from the staged slice (lane-rotated conflict-free 128-bit reads).  Single slice: the row's
       // norm.  Sliced e_dim: the scale is needed before the first slice is converted, so it comes from an ESTIMATE — the
       // first slice's norm times the number of slices — and the true norm is accumulated while the slices are converted
@@ -1047,9 +1165,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
     const long long epi_t0 = clock64();
 #endif
     for (int64_t it = 0; it < my_tiles; ++it) {
-      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t tile = tile_of(it);
       const int64_t row0 = tile * TM;
-      const int rows = (int)min((int64_t)TM, p.N - row0);
+      const int rows = (int)max((int64_t)0, min((int64_t)TM, p.N - row0));
       const int slot = (int)(it & 1);
       RowState st;
       float band = 0.f;
@@ -1135,9 +1253,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
     const long long g_t0 = clock64();
 #endif
     for (int64_t it = 0; it < my_tiles; ++it) {
-      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t tile = tile_of(it);
       const int64_t row0 = tile * TM;
-      const int rows = (int)min((int64_t)TM, p.N - row0);
+      const int rows = (int)max((int64_t)0, min((int64_t)TM, p.N - row0));
       const int slot = (int)(it & 1);
       // Two batches of UH row-steps are kept in flight (software pipeline: the loads of batch b + 1 are issued
       // before batch b is consumed), and the z rows of the first batch — they do not depend on the codes — are
@@ -1278,7 +1396,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
       if (hcount) atomicAdd(p.hist + k, (unsigned long long)hcount);
     }
   }
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+  if (PAIR) {   // no CTA leaves (or frees its TMEM) while the pair's MMAs or remote arrives may still touch it
+    tc::tc_fence_before();
+    tc::cluster_sync_all();
+    tc::tc_fence_after();
+  }
+  if (warp == 1) {
+    if (PAIR) tc::tmem_dealloc_pair(tmem_base, 512);
+    else tc::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 }  // namespace
@@ -1306,12 +1432,52 @@ static int encode_ztile(CUtensorMap* map, const float* z, int64_t N, int D, int 
   return DVQ_OK;
 }
 
+// the operand image as a [bytes / 1024, 256] int32 tensor, box = (256, rows): one half block lands densely in its ring slot
+static int encode_bimg(CUtensorMap* map, const uint8_t* bimg, size_t image_bytes, uint32_t box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DVQ_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(DVQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {256, (cuuint64_t)(image_bytes / 1024)};
+  const cuuint64_t strides[1] = {1024};
+  const cuuint32_t box[2] = {256, box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<uint8_t*>(bimg), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DVQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the operand image (%zu bytes, box rows %u)", (int)r, image_bytes, box_rows);
+  return DVQ_OK;
+}
+
 bool vq_tc_supported(int64_t N, int K, int D) {
   if (N <= 0 || N > 2147483647LL - 256) return false;
   if (D < 16 || D > 512 || (D & (D - 1)) != 0) return false;   // power of two: index math is masks/shifts
   if (USE_ZL && D > DSLICE) return false;
   if (K % 32 != 0 || K < 32 || K > 32704) return false;   // list-mode candidate entries are 10 bits (sub-chunk index + 1 <= 1023)
   return smem_layout(K, D).total <= SMEM_LIMIT;
+}
+
+// CTA-pair kernel (cta_group::2) for this call?  Streamed codebooks only.  Measured at N = 16.8M against the single-CTA
+// kernel, whole call (profiles/README.md): e_dim 512 1.05x (K = 512) .. 1.67x (K = 16 384); e_dim 256 1.11-1.27x from
+// K = 2048 on, 0.93x at K = 1024; e_dim 128 1.06-1.09x from K = 2048 on, 0.91x at K = 512; e_dim 64 0.98-1.00x (one slice
+// per chunk: the accumulator hand-off between the SMs costs what the halved operand stream saves).  Hence: e_dim 512
+// always, e_dim 128 / 256 from K = 2048 on.  DVQ_TC_PAIR=0 turns it off, DVQ_TC_PAIR=1 selects it for every streamed shape.
+bool vq_tc_pair_selected(int64_t N, int K, int D) {
+  static const char* pair_env = getenv("DVQ_TC_PAIR");
+  if (pair_env && pair_env[0] == '0') return false;
+  if (!vq_tc_supported(N, K, D)) return false;
+  const SmemLayout L1 = smem_layout(K, D);
+  if (((K + 255) / 256) * (int)L1.ns <= 2) return false;                 // resident image: the single-CTA kernel
+  if (!(pair_env && pair_env[0] == '1') && !(D >= 512 || (D >= 128 && K >= 2048))) return false;
+  if (smem_layout(K, D, 0, true).total > SMEM_LIMIT) return false;
+  DeviceProps dp;
+  if (device_props(&dp) || dp.sm_count < 2) return false;
+  return N > TM;                                                         // at least two tiles
 }
 
 void vq_tc_layout_info(int K, int D, int* out8) {
@@ -1346,9 +1512,21 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
   static const char* lay_env = getenv("DVQ_TC_LAYOUT");   // experiment: "a st sl" digits, e.g. 123 = 1 A image, 2 staging slots, 3 ring slots
   int ovr = lay_env ? atoi(lay_env) : 0;
   if (ovr && (((K + 255) / 256) * (D / slice_width(D)) <= 2 || smem_layout(K, D, ovr).total > SMEM_LIMIT || ovr / 100 < 1 || ovr / 100 > 2 ||
-              ovr / 10 % 10 < 1 || ovr / 10 % 10 > 2 || ovr % 10 < 2 || ovr % 10 > MAX_BSLOTS))
+              ovr / 10 % 10 < 1 || ovr / 10 % 10 > 2 || ovr % 10 < 2 || ovr % 10 > MAX_BSLOTS_SOLO))
     ovr = 0;   // resident images keep their layout; impossible requests are ignored
-  const SmemLayout L = smem_layout(K, D, ovr);
+  // CTA-pair kernel (cta_group::2) for streamed codebooks: on by default, DVQ_TC_PAIR=0 selects the single-CTA kernel (A/B runs).
+  // It needs an even number of SMs to pair up and at least one full pair of tiles.
+  static const char* ce_env = getenv("DVQ_TC_CE");
+  static const char* st_env = getenv("DVQ_TC_ST");
+  int pair_ovr = lay_env ? atoi(lay_env) : 0;   // the pair kernel accepts rings of up to MAX_BSLOTS slots
+  if (pair_ovr && (pair_ovr / 100 < 1 || pair_ovr / 100 > 2 || pair_ovr / 10 % 10 < 1 || pair_ovr / 10 % 10 > 2 || pair_ovr % 10 < 2 || pair_ovr % 10 > MAX_BSLOTS ||
+                   smem_layout(K, D, pair_ovr, true).total > SMEM_LIMIT))
+    pair_ovr = 0;
+  const SmemLayout L1 = smem_layout(K, D, ovr);
+  const bool streamed = ((K + 255) / 256) * (int)L1.ns > 2;
+  const bool pair = vq_tc_pair_selected(N, K, D);
+  const SmemLayout L = pair ? smem_layout(K, D, pair_ovr, true) : L1;
+  const size_t image_bytes = (size_t)((K + 255) / 256) * L1.ns * L1.bchunk_bytes;   // the same for both image layouts
   if (codebook_cached) {
     // DVQ_CODEBOOK_CACHED: CbMeta and the operand image in `bop` are those of this codebook; only the per-call
     // counters and bin tables are reset
@@ -1356,10 +1534,10 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
     DVQ_CUDA_CHECK(cudaGetLastError());
     count_launch();
   } else {
-    tc_cb_stats_kernel<<<1, 256, 0, s>>>(ee, K, D, cb, counters, zero_ints, zero_n);
+    tc_cb_stats_kernel<<<1, 256, 0, s>>>(ee, K, D, cb, counters, zero_ints, zero_n, pair);
     DVQ_CUDA_CHECK(cudaGetLastError());
-    DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, (size_t)((K + 255) / 256) * L.ns * L.bchunk_bytes, s));
-    tc_cb_image_kernel<<<(K * 32 + 255) / 256, 256, 0, s>>>(E, ee, K, D, cb, bimg);
+    DVQ_CUDA_CHECK(cudaMemsetAsync(bimg, 0, image_bytes, s));
+    tc_cb_image_kernel<<<(K * 32 + 255) / 256, 256, 0, s>>>(E, ee, K, D, cb, bimg, pair);
     DVQ_CUDA_CHECK(cudaGetLastError());
     count_launch(2);
   }
@@ -1370,33 +1548,54 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
     rc = encode_ztile(&p.ztile, z, N, D, (int)L.ds);
     if (rc) return rc;
   }
+  memset(p.bmap, 0, sizeof(p.bmap));
+  if (pair) {
+    rc = encode_bimg(&p.bmap[0], bimg, image_bytes, L.bslice_bytes / 1024);
+    if (!rc) rc = encode_bimg(&p.bmap[1], bimg, image_bytes, L.bchunk_bytes / 1024);
+    if (rc) return rc;
+  }
   p.z = z; p.E = E; p.bimg = bimg; p.cb = cb; p.N = N; p.K = K; p.D = D; p.train = train;
   p.zq = z_q; p.idx = idx; p.hist = hist; p.sse = sse; p.counters = counters; p.row_list = row_list; p.cand_list = cand_list; p.cand_gshift = vq_tc_cand_gshift(K);
-  p.layout_ovr = ovr;
+  p.layout_ovr = pair ? pair_ovr : ovr;
   p.stats = reinterpret_cast<unsigned long long*>(counters + 8);
   p.ntiles = (N + TM - 1) / TM;
   const size_t smem = L.total + 128;
-  const int64_t grid = p.ntiles < dp.sm_count ? p.ntiles : dp.sm_count;
+  int64_t grid = p.ntiles < dp.sm_count ? p.ntiles : dp.sm_count;
+  if (pair) {   // clusters of two CTAs: one per tile pair, at most one per TPC
+    const int64_t units = (p.ntiles + 1) / 2;
+    grid = 2 * (units < dp.sm_count / 2 ? units : dp.sm_count / 2);
+  }
   // Converters join the filter as a fourth warp per TMEM lane quarter (DVQ_TC_CE=1; needs a streamed codebook and a
   // double-buffered A image).  It paid +4 % at e_dim 64, K >= 4096 while the filter was the bound; with the list-mode
   // early-out the filter is cheap and the variant is 5 % behind the default there, so it is not selected automatically.
-  static const char* ce_env = getenv("DVQ_TC_CE");
-  const bool streamed = ((K + 255) / 256) * (int)L.ns > 2;
   const bool ce = streamed && L.a_bufs == 2 && ce_env && ce_env[0] == '1';
 #define DVQ_LAUNCH_TC(DT_, TR_, LS_, CE_, ST_)                                                                              \
   do {                                                                                                                 \
     DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<DT_, TR_, LS_, CE_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     vq_tc_kernel<DT_, TR_, LS_, CE_, ST_><<<(unsigned)grid, NTHREADS, smem, s>>>(p);                                        \
   } while (0)
+#define DVQ_LAUNCH_TC_PAIR(TR_, LS_, CE_, ST_)                                                                              \
+  do {                                                                                                                 \
+    DVQ_CUDA_CHECK(cudaFuncSetAttribute(vq_tc_kernel<0, TR_, LS_, CE_, ST_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    cudaLaunchConfig_t cfg = {};                                                                                       \
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;     \
+    cudaLaunchAttribute at[1];                                                                                         \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                                    \
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                                 \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                                                  \
+    DVQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, vq_tc_kernel<0, TR_, LS_, CE_, ST_, true>, p));                             \
+  } while (0)
 #define DVQ_LAUNCH_TC_GENERIC(TR_, LS_)                                      \
   do {                                                                       \
-    if (st) DVQ_LAUNCH_TC(0, TR_, LS_, false, true);                         \
+    if (pair && st) DVQ_LAUNCH_TC_PAIR(TR_, LS_, false, true);               \
+    else if (pair && ce) DVQ_LAUNCH_TC_PAIR(TR_, LS_, true, false);          \
+    else if (pair) DVQ_LAUNCH_TC_PAIR(TR_, LS_, false, false);               \
+    else if (st) DVQ_LAUNCH_TC(0, TR_, LS_, false, true);                    \
     else if (ce) DVQ_LAUNCH_TC(0, TR_, LS_, true, false);                    \
     else DVQ_LAUNCH_TC(0, TR_, LS_, false, false);                           \
   } while (0)
   // two-sub-chunk filter with the epilogue-heavy register split (DVQ_TC_ST=1; streamed codebooks only).  Measured
   // within +-2 % of the default at every K >= 2048 shape of the sweep, so it is not selected automatically.
-  static const char* st_env = getenv("DVQ_TC_ST");
   const bool st = streamed && st_env && st_env[0] == '1';
   const bool list = p.cand_gshift < 0;
   if (D == 64 && !list && !streamed) {
@@ -1407,6 +1606,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
     if (train) DVQ_LAUNCH_TC_GENERIC(true, true); else DVQ_LAUNCH_TC_GENERIC(false, true);
   }
 #undef DVQ_LAUNCH_TC_GENERIC
+#undef DVQ_LAUNCH_TC_PAIR
 #undef DVQ_LAUNCH_TC
   DVQ_CUDA_CHECK(cudaGetLastError());
   count_launch();

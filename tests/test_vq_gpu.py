@@ -439,7 +439,7 @@ sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "d-vqvae_b200"))
 import dvq
 from dvq import _cabi
 from oracle import vq_oracle as vo
-for K, D in ((4096, 64), (2048, 32), (1024, 128)):
+for K, D in ((4096, 64), (2048, 32), (1024, 128), (2048, 256), (544, 128), (1024, 512)):
     N = 30000 + 19
     E = vo.default_codebook(K, D, 51); z = vo.normal_latents(N, D, 52)
     z[::199] = 0.0
@@ -460,12 +460,17 @@ print("VARIANT_OK")
 """
 
 
-@pytest.mark.parametrize("env", [{"DVQ_TC_CE": "1"}, {"DVQ_TC_ST": "1"}], ids=["converters_join_filter", "two_subchunk_filter"])
+@pytest.mark.parametrize("env", [{"DVQ_TC_CE": "1"}, {"DVQ_TC_ST": "1"}, {"DVQ_TC_PAIR": "0"}, {"DVQ_TC_PAIR": "1"},
+                                 {"DVQ_TC_PAIR": "1", "DVQ_TC_CE": "1"}, {"DVQ_TC_PAIR": "1", "DVQ_TC_ST": "1"}],
+                         ids=["converters_join_filter", "two_subchunk_filter", "single_cta_only", "cta_pair_everywhere",
+                              "cta_pair_converters_join", "cta_pair_two_subchunk"])
 def test_streamed_kernel_variants_behind_env_switches(env):
-    """The streamed-codebook kernel has two optional variants selected by environment switches that are read once
+    """The streamed-codebook kernel has optional variants selected by environment switches that are read once
     per process (DVQ_TC_CE: the converter warps filter as a fourth warp per TMEM lane quarter; DVQ_TC_ST: epilogue
-    warps with 104 registers filter two sub-chunks per step).  Each must agree with the all-FP32 kernel under the
-    same parity rule as the default variant; a fresh interpreter per variant."""
+    warps with 104 registers filter two sub-chunks per step; DVQ_TC_PAIR: 0 = never use the CTA-pair (cta_group::2)
+    kernel, 1 = use it for every streamed shape, default = for e_dim >= 128).  Each must agree with the all-FP32
+    kernel under the same parity rule as the default variant; a fresh interpreter per variant.  N gives an odd
+    number of row tiles, so the pair kernel's last tile pair has an empty second half; K = 544 a ragged last chunk."""
     import os
     import subprocess
     import sys
