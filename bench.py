@@ -26,6 +26,7 @@ Weak scaling: every rank holds its own 4M-row shard, codebook replicated, one al
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -241,33 +242,38 @@ def run_secondary(torch, tdist, dvq, dev, rank, world, fence):
             ms = float(t.item())
         return ms
 
-    # ---- config 4 corner: K = 16384, e_dim = 128, 16 777 216 latents in total (rows sharded), train path ----
-    try:
-        K4, D4, N4 = 16384, 128, 16777216 // world
-        g = torch.Generator(device=dev).manual_seed(4000 + rank)
-        cg = torch.Generator(device=dev).manual_seed(4000)
-        vq4 = dvq.VectorQuantizer(K4, D4, BETA, AL).to(dev)
-        vq4.onehot_limit_bytes = 0
-        with torch.no_grad():
-            vq4.embedding.weight.copy_((torch.rand(K4, D4, device=dev, generator=cg) * 2 - 1) / K4)
-        if world > 1:
-            dvq.dist.shard_module(vq4)
-        z4 = torch.randn(N4, D4, device=dev, generator=g)
-
-        def step4():
+    # ---- config 4 corners: K = 16384 at e_dim 128 and 512, 16 777 216 latents in total (rows sharded), train path.  Both are
+    # streamed codebooks on the CTA-pair (cta_group::2) kernel ----
+    for K4, D4 in ((16384, 128), (16384, 512)):
+        key = "config4_k%d_d%d" % (K4, D4)
+        try:
+            N4 = 16777216 // world
+            g = torch.Generator(device=dev).manual_seed(4000 + rank)
+            cg = torch.Generator(device=dev).manual_seed(4000)
+            vq4 = dvq.VectorQuantizer(K4, D4, BETA, AL).to(dev)
+            vq4.onehot_limit_bytes = 0
             with torch.no_grad():
-                return vq4(z4, True)
-        ms = timed(step4)
-        tf = 2.0 * N4 * world * K4 * D4 / (ms * 1e-3) / 1e12
-        out["config4_k16384_d128"] = {
-            "metric": METRIC, "value": N4 * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "rows_per_gpu": N4, "n_e": K4, "e_dim": D4,
-            "undecided_rows_rank0": vq4.last_counters(N4)[0],
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_sus * world, "unit": "TFLOP/s", "frac": tf / (bf16_sus * world),
-                         "what": "2*N*K*e_dim of the whole call (norm pre-pass + filter + exact refine + finalize) over the sustained BF16 peak x GPUs"}}
-        del z4, vq4
-        torch.cuda.empty_cache()
-    except Exception as e:                                  # noqa: BLE001
-        out["config4_k16384_d128"] = {"error": repr(e)}
+                vq4.embedding.weight.copy_((torch.rand(K4, D4, device=dev, generator=cg) * 2 - 1) / K4)
+            if world > 1:
+                dvq.dist.shard_module(vq4)
+            z4 = torch.randn(N4, D4, device=dev, generator=g)
+
+            def step4():
+                with torch.no_grad():
+                    return vq4(z4, True)
+            ms = timed(step4, iters=3 if D4 <= 128 else 2)
+            tf = 2.0 * N4 * world * K4 * D4 / (ms * 1e-3) / 1e12
+            plan = (ctypes.c_int * 8)()
+            dvq._cabi.lib.dvq_debug_tc_pair_layout(N4, K4, D4, plan)
+            out[key] = {
+                "metric": METRIC, "value": N4 * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "rows_per_gpu": N4, "n_e": K4, "e_dim": D4,
+                "undecided_rows_rank0": vq4.last_counters(N4)[0], "kernel": "cta_pair (cta_group::2)" if plan[0] else "single CTA",
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_sus * world, "unit": "TFLOP/s", "frac": tf / (bf16_sus * world),
+                             "what": "2*N*K*e_dim of the whole call (filter + exact refine + finalize) over the sustained BF16 peak x GPUs"}}
+            del z4, vq4
+            torch.cuda.empty_cache()
+        except Exception as e:                                  # noqa: BLE001
+            out[key] = {"error": repr(e)}
 
     # ---- PointNet encoder: C = 4, P = 3000, 4096 clouds per GPU, default (tcgen05) path ----
     try:

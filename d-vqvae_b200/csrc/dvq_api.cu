@@ -122,6 +122,13 @@ int dvq_debug_tc_layout(int K, int D, int* out8) {
   return DVQ_OK;
 }
 
+int dvq_debug_tc_pair_layout(long long N, int K, int D, int* out8) {
+  if (!out8) return fail(DVQ_ERR_BAD_ARG, "out8 is NULL");
+  if (K <= 0 || D <= 0) return fail(DVQ_ERR_BAD_SHAPE, "need K > 0, D > 0");
+  vq_tc_pair_layout_info((int64_t)N, K, D, out8);
+  return DVQ_OK;
+}
+
 int dvq_profile_enable(int on) {
   g_prof_on = on != 0;
   for (int i = 0; i < kStages; ++i) g_prof_n[i] = 0;

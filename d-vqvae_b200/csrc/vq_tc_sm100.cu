@@ -597,8 +597,15 @@ __device__ __forceinline__ void filter_subchunk2(uint32_t (&va)[32], uint32_t (&
   float ka[32], kb[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) { ka[j] = __uint_as_float(va[j]); kb[j] = __uint_as_float(vb[j]); }
-  const float m1a = fminf(subchunk_min(ka), st.m1);
-  const float m1b = fminf(subchunk_min(kb), m1a);
+  const float ma = subchunk_min(ka), mb = subchunk_min(kb);   // two independent min trees
+  if (LIST) {
+    // the early-out of filter_subchunk for both sub-chunks at once (see there): nothing below the running threshold in
+    // either, for every row of the warp -> no new minimum, no indicator bit, no state change
+    const bool need = fma_sat(fminf(ma, mb), -BIG, fmaf(st.m1, BIG, band_big)) != 0.f;
+    if (!__any_sync(0xffffffffu, need)) return;
+  }
+  const float m1a = fminf(ma, st.m1);
+  const float m1b = fminf(mb, m1a);
   const bool reset_a = st.m1 - m1a > band, reset_b = m1a - m1b > band;
   const uint32_t bits_a = subchunk_bits(ka, fmaf(m1a, BIG, band_big));
   const uint32_t bits_b = subchunk_bits(kb, fmaf(m1b, BIG, band_big));
@@ -1475,9 +1482,18 @@ bool vq_tc_pair_selected(int64_t N, int K, int D) {
   if (((K + 255) / 256) * (int)L1.ns <= 2) return false;                 // resident image: the single-CTA kernel
   if (!(pair_env && pair_env[0] == '1') && !(D >= 512 || (D >= 128 && K >= 2048))) return false;
   if (smem_layout(K, D, 0, true).total > SMEM_LIMIT) return false;
-  DeviceProps dp;
-  if (device_props(&dp) || dp.sm_count < 2) return false;
   return N > TM;                                                         // at least two tiles
+}
+
+// dvq_debug_tc_pair_layout: out8 = { CTA-pair kernel selected for (N, K, D) (0/1), slice width, slices, A images, ring
+// slots, z staging slots, dynamic shared memory, codes per ring slot } of the pair layout (host-only)
+void vq_tc_pair_layout_info(int64_t N, int K, int D, int* out8) {
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (!vq_tc_supported(N > 0 ? N : 1, K, D)) return;
+  const SmemLayout L = smem_layout(K, D, 0, true);
+  out8[0] = vq_tc_pair_selected(N, K, D) ? 1 : 0;
+  out8[1] = (int)L.ds; out8[2] = (int)L.ns; out8[3] = (int)L.a_bufs; out8[4] = (int)L.nslots; out8[5] = (int)L.nstage;
+  out8[6] = (int)L.total + 128; out8[7] = (int)L.bcodes;
 }
 
 void vq_tc_layout_info(int K, int D, int* out8) {
@@ -1524,7 +1540,7 @@ int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int
     pair_ovr = 0;
   const SmemLayout L1 = smem_layout(K, D, ovr);
   const bool streamed = ((K + 255) / 256) * (int)L1.ns > 2;
-  const bool pair = vq_tc_pair_selected(N, K, D);
+  const bool pair = vq_tc_pair_selected(N, K, D) && dp.sm_count >= 2;
   const SmemLayout L = pair ? smem_layout(K, D, pair_ovr, true) : L1;
   const size_t image_bytes = (size_t)((K + 255) / 256) * L1.ns * L1.bchunk_bytes;   // the same for both image layouts
   if (codebook_cached) {

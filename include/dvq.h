@@ -86,6 +86,13 @@ DVQ_API int dvq_vq_set_refine(int mode, long long pair_cap);
  * memory (0/1) }.  Used by tests/test_cabi_symbols.py to pin the per-shape choices. */
 DVQ_API int dvq_debug_tc_layout(int K, int D, int* out8);
 
+/* Diagnostic (host-only): streamed codebooks (the operand image does not fit shared memory) with e_dim 512, or e_dim
+ * 128 / 256 from K = 2048 on, run on CTA pairs (clusters of two CTAs, tcgen05 cta_group::2: one M = 256 MMA over both
+ * SMs' row tiles, each CTA streaming half of every operand block).  out8 = { pair kernel selected for (N, K, D) (0/1;
+ * honours DVQ_TC_PAIR=0/1), e_dim slice width, slices per row, A images, ring slots (2-8), z staging slots, dynamic
+ * shared memory in bytes, codes per ring slot (128) } of the pair kernel's plan. */
+DVQ_API int dvq_debug_tc_pair_layout(long long N, int K, int D, int* out8);
+
 /* Diagnostic used by tests/test_tc_probe_gpu.py: run `ksteps` tcgen05.mma (M=128, N=n_cols,
  * kind::f16) on caller-built shared-memory operand images and dump the [128,n_cols] fp32
  * accumulator.  strides = {a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep} in bytes; *err (device

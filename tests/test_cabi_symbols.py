@@ -137,6 +137,35 @@ def test_tc_shared_memory_plan_per_shape():
     assert plan(500, 64)["ok"] == 0 and plan(512, 48)["ok"] == 0 and plan(32768, 64)["ok"] == 0
 
 
+def test_tc_pair_kernel_selection_rule():
+    """Host-only view of the CTA-pair (cta_group::2) kernel's selection and shared-memory plan (dvq_debug_tc_pair_layout):
+    streamed codebooks at e_dim 512, and at e_dim 128 / 256 from K = 2048 on (the shapes where it measured ahead of
+    the single-CTA kernel); never for a resident operand image (config 2) or a single row tile; every selected
+    shape's plan fits the 227 KB budget with half-block ring slots (128 codes)."""
+    import os
+    from dvq import _cabi
+    if os.environ.get("DVQ_TC_PAIR"):
+        pytest.skip("DVQ_TC_PAIR overrides the rule")
+
+    def plan(N, K, D):
+        out = (ctypes.c_int * 8)()
+        _cabi.check(_cabi.lib.dvq_debug_tc_pair_layout(N, K, D, out), "dvq_debug_tc_pair_layout")
+        return dict(zip(("pair", "ds", "ns", "a_bufs", "nslots", "nstage", "bytes", "bcodes"), list(out)))
+
+    N = 1 << 20
+    for K in (512, 1024, 2048, 4096, 8192, 16384):
+        for D in (64, 128, 256, 512):
+            p = plan(N, K, D)
+            want = D == 512 or (D >= 128 and K >= 2048)
+            assert p["pair"] == int(want), (K, D, p)
+            if want:
+                assert p["bytes"] <= 227 * 1024 and p["bcodes"] == 128 and 2 <= p["nslots"] <= 8 and p["ds"] * p["ns"] == D
+    assert plan(N, 512, 64)["pair"] == 0              # config 2: resident image
+    assert plan(128, 16384, 512)["pair"] == 0         # one row tile: nothing to pair
+    assert plan(129, 16384, 512)["pair"] == 1
+    assert plan(N, 128, 256)["pair"] == 0             # the grasp codebooks (K = 128): single-CTA kernel
+
+
 def test_module_caches_survive_deepcopy_and_see_reloaded_weights():
     """cached device-pointer structs made the modules unpicklable, and the fold / pack caches could go
     stale.  CPU-only checks of the host logic: deepcopy / pickle work, load_state_dict invalidates the caches."""
