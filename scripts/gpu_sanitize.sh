@@ -6,7 +6,7 @@ import sys; sys.path.insert(0, "d-vqvae_b200"); sys.path.insert(0, ".")
 import numpy as np, torch, dvq
 from dvq import _cabi
 torch.manual_seed(0)
-for K, D, N in ((512, 64, 1000), (512, 128, 700), (1024, 256, 300), (2048, 512, 260)):
+for K, D, N in ((512, 64, 1000), (512, 128, 700), (1024, 256, 300), (2048, 512, 260), (2048, 128, 300), (4096, 256, 513)):
     vq = dvq.VectorQuantizer(K, D, 0.25, 1.0).cuda(); vq.onehot_limit_bytes = 0
     z = torch.randn(N, D, device="cuda")
     with torch.no_grad():
