@@ -716,6 +716,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
     const int sc0 = (wq + EPQX - 1) % EPQX;
     for (int c = 0; c < nchunks; ++c, ++q) {
       const uint32_t t = q & 1u;
+#ifdef DVQ_ACC_MBAR   // experiment: every filter warp waits on the commit mbarrier itself (no lock-step with its sibling warps)
+      if (resident) wait_or_trap(BAR(B_ACC_FULL, t), (q >> 1) & 1u, err_out, ERR_ACC_FULL);
+      else
+#endif
       if (wq == 0) nb_sync(NB_ACC_FULL_OWN + (int)t, NB_ACC_OWN_THREADS);
       else nb_sync(NB_ACC_FULL_HLP + (int)t, NB_ACC_HLP_THREADS);
       tc::tc_fence_after();
@@ -964,6 +968,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
           // Streamed codebooks: the completion of this chunk is awaited and relayed by warp 3, so that the next
           // chunk's MMAs are issued while these execute (+2-3 % at K = 16 384).  Resident image (two chunks per
           // tile): this warp relays itself — the extra hop measured ~1.5 % slower there.
+#ifndef DVQ_ACC_MBAR
           if (resident) {
             wait_or_trap(BAR(B_ACC_FULL, t), (q >> 1) & 1u, err_out, ERR_ACC_FULL);
             TRACE(0, 3, c & 1);
@@ -971,6 +976,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
             nb_arrive(NB_ACC_FULL_HLP + (int)t, NB_ACC_HLP_THREADS);
             nb_arrive(NB_ACC_FULL_OWN + (int)t, NB_ACC_OWN_THREADS);
           }
+#endif
         }
       }
 #ifdef DVQ_TC_STATS
