@@ -219,7 +219,7 @@ __device__ __forceinline__ uint32_t float_key(float d) {
 }
 
 template <int DS>
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
+__global__ void __launch_bounds__(PAIR_THREADS, DS <= 32 ? 2 : 1)
 refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ ee, int K, int D,
                     const float* __restrict__ zq, unsigned long long* __restrict__ idx64, const int* __restrict__ row_list,
                     const int* __restrict__ ovf_last, const int* __restrict__ pairs, const int* __restrict__ counters,
@@ -413,9 +413,16 @@ int launch_vq_refine_binned(const float* z, const float* E, const float* ee, int
   const long long pair_cap = (cap_override > 0 && cap_override < 2 * (long long)N) ? cap_override : 2 * (long long)N;
   const int* ovf_last = row_list + (N - 1);
   unsigned long long* idx64 = reinterpret_cast<unsigned long long*>(idx);
-  const int pair_grid = dp.sm_count;
+  // slice width of the pairs kernel: a lane keeps DS floats of its code row in registers.  DS = 64 (168 registers, one CTA
+  // of 12 warps per SM) re-reads a code row half as often, DS = 32 (80 registers) fits two CTAs per SM: measured at
+  // N = 2M-4M, refine stage: e_dim 128 / 256 / 512 at K = 16 384 / 16 384 / 4096: 0.60 -> 0.44, 1.85 -> 1.37, 2.32 -> 1.71 ms
+  // with DS = 32; e_dim 64 (one slice at DS = 64: the code row stays in registers for the whole work item): 0.15 -> 0.19 ms at
+  // K = 2048.  Hence 32 from e_dim 128 on.  DVQ_REFINE_DS=32|64 overrides (A/B runs).
+  static const char* ds_env = getenv("DVQ_REFINE_DS");
+  const int ds_want = ds_env ? atoi(ds_env) : (D >= 128 ? 32 : 64);
+  const int DS = D < 64 ? D : (ds_want == 32 ? 32 : 64);
+  const int pair_grid = dp.sm_count * (DS <= 32 && D >= 64 ? 2 : 1);
   const int pair_warps = pair_grid * (PAIR_THREADS / 32);
-  const int DS = D < 64 ? D : 64;
 
   refine_prep_kernel<<<dp.sm_count, PREP_THREADS, 0, s>>>(z, D, K, z_q, idx64, row_list, cand_list, ovf_last, counters, bt, list_mode);
   DVQ_CUDA_CHECK(cudaGetLastError());
