@@ -239,6 +239,13 @@ refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, co
   const int items = s_items[nbins];
   float* zs = smem_f + warp * 2 * RB * DS;   // two halves: one being read, one being filled
   const int ns = D / DS;
+  // sliced e_dim: the 32 code rows' slices are staged too ([32][DS + 4] floats, single-buffered: filled by coalesced
+  // cp.async for the next step as soon as every lane has copied its own row into registers — conflict-free 128-bit loads —,
+  // i.e. under this step's FMAs).
+  // Each lane fetching its own row straight from global memory — 32 different lines per load instruction — took two
+  // thirds of the LSU data pipe, which the ncu capture showed to be the kernel's bound (74 % busy, FMA pipe 24 %).
+  constexpr int EP = DS + 4;
+  float* es = smem_f + NW * 2 * RB * DS + warp * 32 * EP;
   for (int item = blockIdx.x * NW + warp; item < items; item += gridDim.x * NW) {
     // bucket of this item: the last b with item_start[b] <= item
     int lo = 0, hi = nbins;   // invariant: s_items[lo] <= item < s_items[hi]
@@ -272,6 +279,17 @@ refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, co
         zz_ = zq[row_ * D];
       }
     };
+    auto stage_e = [&](int sl) {   // (no commit of its own)
+#pragma unroll
+      for (int k = 0; k < DS / 4; ++k) {
+        const int f = k * 32 + lane;
+        const int cl = f / (DS / 4), c4 = f - cl * (DS / 4);
+        const bool cv = b * 32 + cl < K;
+        const float* src = E + (size_t)(cv ? b * 32 + cl : 0) * D + sl * DS + c4 * 4;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(es + cl * EP + c4 * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(cv ? 16 : 0) : "memory");
+      }
+    };
     auto stage_z = [&](int64_t row_, int sl, int buf) {
 #pragma unroll
       for (int k = 0; k < ZL; ++k) {
@@ -288,6 +306,7 @@ refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, co
     float zz, zz_n;
     int buf = 0;
     fetch_rows(p0, row, zz);
+    if (ns > 1) stage_e(0);   // same group as the first z rows
     stage_z(row, 0, 0);
     for (int p = p0; p < p1; p += RB) {
       const int nb = min(RB, p1 - p);
@@ -296,19 +315,26 @@ refine_pairs_kernel(const float* __restrict__ z, const float* __restrict__ E, co
 #pragma unroll
       for (int r = 0; r < RB; ++r) acc[r] = 0.f;
       for (int sl = 0; sl < ns; ++sl) {
-        if (ns > 1) {
-#pragma unroll
-          for (int d = 0; d < DS; d += 4) {
-            const float4 v = ldg4(erow + sl * DS + d);
-            e[d] = v.x; e[d + 1] = v.y; e[d + 2] = v.z; e[d + 3] = v.w;
-          }
-        }
         __syncwarp();   // the previous step's reads of the other half are done
         if (sl + 1 < ns) stage_z(row, sl + 1, buf ^ 1);
         else if (p + RB < p1) stage_z(row_n, 0, buf ^ 1);
         else asm volatile("cp.async.commit_group;" ::: "memory");   // keep one group per step
-        asm volatile("cp.async.wait_group 1;" ::: "memory");         // this step's rows have landed
+        asm volatile("cp.async.wait_group 1;" ::: "memory");         // this step's rows (and code slices) have landed
         __syncwarp();
+        if (ns > 1) {
+          const float* eb = es + lane * EP;
+#pragma unroll
+          for (int d = 0; d < DS; d += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(eb + d);
+            e[d] = v.x; e[d + 1] = v.y; e[d + 2] = v.z; e[d + 3] = v.w;
+          }
+          __syncwarp();   // every lane has its row: the buffer takes the next step's slices (a group of its own, older than
+                          // the next step's z group, so that step's wait_group 1 covers it)
+          if (sl + 1 < ns || p + RB < p1) {
+            stage_e(sl + 1 < ns ? sl + 1 : 0);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+          }
+        }
         const float* zb = zs + buf * RB * DS;
         buf ^= 1;
 #pragma unroll
@@ -428,7 +454,7 @@ int launch_vq_refine_binned(const float* z, const float* E, const float* ee, int
   DVQ_CUDA_CHECK(cudaGetLastError());
   refine_scatter_kernel<<<dp.sm_count, PREP_THREADS, 0, s>>>(K, cand_list, counters, bt, pairs, pair_cap, list_mode, pair_warps);
   DVQ_CUDA_CHECK(cudaGetLastError());
-  const size_t smem = (size_t)(PAIR_THREADS / 32) * 2 * RB * DS * sizeof(float);
+  const size_t smem = (size_t)(PAIR_THREADS / 32) * (2 * RB * DS + (D > DS ? 32 * (DS + 4) : 0)) * sizeof(float);
 #define DVQ_LAUNCH_PAIRS(DS_)                                                                                              \
   do {                                                                                                                     \
     DVQ_CUDA_CHECK(cudaFuncSetAttribute(refine_pairs_kernel<DS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
