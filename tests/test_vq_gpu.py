@@ -166,10 +166,11 @@ def _assert_rows_within_band(z, E, idx_a, idx_b, max_rows=200000):
     return n_mis
 
 
-@pytest.mark.parametrize("N,K,D", [(16777216, 16384, 64), (4194304, 4096, 256)])
+@pytest.mark.parametrize("N,K,D", [(16777216, 16384, 64), (4194304, 4096, 256), (2097152 + 128, 2048, 512)])
 def test_config4_corners_full_size_all_rows(N, K, D):
-    """Two corners of BASELINE config 4 at full per-GPU size (16.8M rows on one GPU; the 4-GPU shard of the
-    e_dim 256 shape): every row of the tcgen05 path against the all-FP32 kernel (band rule on differing rows),
+    """Corners of BASELINE config 4 at full per-GPU size (16.8M rows on one GPU on the single-CTA streamed kernel; the
+    4-GPU shard of an e_dim 256 shape and the 8-GPU shard (+ one tile: an odd tile count) of an e_dim 512 shape, both on
+    the CTA-pair kernel): every row of the tcgen05 path against the all-FP32 kernel (band rule on differing rows),
     z_q / histogram / loss consistency on all rows."""
     from dvq import _cabi
     gen = torch.Generator(device="cuda").manual_seed(4000 + K + D)
