@@ -296,7 +296,7 @@ int dvq_vq_read_counters(const void* workspace, int64_t N, int K, int D, int fla
                                 cudaMemcpyDeviceToHost));
       static const char* ev[5][4] = {{"mma.a_full", "mma.acc_empty", "mma.issued", "mma.complete"},
                                      {"own.acc_full", "own.chunk_done", "own.fin_full", "own.sidx_out"},
-                                     {"hlp.acc_full", "hlp.chunk_done", "hlp.fin_out", ""},
+                                     {"hlp.acc_full", "hlp.chunk_done", "hlp.fin_out", "hlp.stage_freed"},
                                      {"cnv.stage_full", "cnv.pass1_done", "cnv.a_empty", "cnv.a_full_out"},
                                      {"gth.sidx_full", "gth.done", "", ""}};
       long long base = tr[(0 * 8 + 0) * 8 + 0];

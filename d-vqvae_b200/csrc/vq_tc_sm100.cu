@@ -766,6 +766,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_tc_kernel(const __grid_constan
           nb_arrive(NB_ACC_EMPTY + (int)t, NB_ACC_THREADS);
         }
       }
+      if (wq == 1 && r < 32) TRACE(2, 3, c & 1);   // (stats builds) after the stage was handed back
     }
     if (LIST && st.ncand > 3) st.cand = CAND_OVERFLOW;   // an entry was shifted out: the refine scans every code of this row
   };
