@@ -186,11 +186,14 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D, int ovr = 0, boo
     smem_place(L, K);
     return L;
   }
-  if (!pair && nchunks == 2 && L.ns == 2) {
-    // K <= 512 at e_dim 128: four blocks per tile.  Measured at N = 16.8 M: one A image, one staging slot and a ring of
-    // three 6.9 ms, the two-of-everything layout the general rule picks 8.0 ms (K = 1024 at e_dim 128, eight blocks:
-    // 8.9 vs 8.4 ms the other way round)
-    L.a_bufs = 1; L.nstage = 1; L.nslots = 3;
+  if (!pair && ((nchunks == 2 && (L.ns == 2 || L.ns == 4)) || (nchunks == 4 && L.ns == 2))) {
+    // Few blocks per tile at e_dim 128 / 256: measured layouts (N = 16.8 M, filter kernel; profiles/README.md).  A tile is short,
+    // so what counts is the per-tile chain load -> convert -> MMA -> filter, and a smaller footprint leaves the gather more L1:
+    //   K <= 512, e_dim 128 (4 blocks):  (1, 1, 2) 5.17 ms, (2, 1, 2) 5.21, (1, 1, 3) 5.34, (1, 2, 2) 5.66, (2, 2, 2) 6.22
+    //   K <= 512, e_dim 256 (8 blocks):  (1, 1, 2) 11.49 ms, (1, 2, 2) 13.43 / 13.48
+    //   K = 1024, e_dim 128 (8 blocks):  (2, 1, 2) 6.23 ms, (2, 2, 2) 6.62, (1, 2, 2) 6.98, (1, 1, 2) 7.28, (1, 1, 3) 7.35
+    const bool two_a = nchunks == 4;   // K = 1024 at e_dim 128: the second A image pays once a tile has four chunks
+    L.a_bufs = two_a ? 2 : 1; L.nstage = 1; L.nslots = 2;
     if (smem_place(L, K) <= SMEM_LIMIT) return L;
   }
   uint32_t best_score = 0, best_a = 1, best_st = 1, best_sl = 2;
