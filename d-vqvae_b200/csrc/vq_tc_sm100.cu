@@ -196,6 +196,23 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int D, int ovr = 0, boo
     L.a_bufs = two_a ? 2 : 1; L.nstage = 1; L.nslots = 2;
     if (smem_place(L, K) <= SMEM_LIMIT) return L;
   }
+  if (pair) {
+    // CTA-pair kernel, measured layouts (N = 4M, filter kernel; profiles/r02_ab_pair_layouts.jsonl); everything else
+    // follows the general rule below, which was at or within 1 % of the best layout tried:
+    //   e_dim 512, K >= 4096: one z staging slot and a ring of five (1, 1, 5) instead of (1, 2, 4):
+    //                         K = 4096 19.5 vs 20.0 ms, K = 8192 35.3 vs 37.0, K = 16 384 64.2 vs 70.0 (K <= 2048: 6-13 % slower)
+    //   e_dim 256, K = 4096: one A image, two staging slots, ring of four (1, 2, 4) instead of (2, 1, 2): 7.17 vs 7.93 ms
+    //                         (N = 16.8M: 35.3 vs 38.7); K = 8192: 13.8 vs 14.2 at N = 4M but 62.8 vs 61.8 at N = 16.8M,
+    //                         K = 2048 and K = 16 384 2 % slower: not applied there
+    if (L.ns == 16 && nchunks >= 16) {
+      L.a_bufs = 1; L.nstage = 1; L.nslots = 5;
+      if (smem_place(L, K) <= SMEM_LIMIT) return L;
+    }
+    if (L.ns == 4 && nchunks >= 16 && nchunks < 32) {
+      L.a_bufs = 1; L.nstage = 2; L.nslots = 4;
+      if (smem_place(L, K) <= SMEM_LIMIT) return L;
+    }
+  }
   uint32_t best_score = 0, best_a = 1, best_st = 1, best_sl = 2;
   for (uint32_t a = 2; a >= 1; --a)
     for (uint32_t st = 2; st >= 1; --st)
