@@ -57,15 +57,22 @@ for K, D in sorted(shapes, key=lambda s: (s[1], s[0])):
         torch.cuda.synchronize(dev)
         if world > 1:
             tdist.barrier(); torch.cuda.synchronize(dev)
-        _cabi.lib.dvq_profile_enable(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.iters):
-            r = m(z, True)
-        e1.record(); torch.cuda.synchronize(dev)
-        prof_ms, _ = _cabi.profile_mean()
-        _cabi.lib.dvq_profile_enable(0)
-    ms = e0.elapsed_time(e1) / args.iters
+        # two timed passes, the faster one is kept: the first pass of a new row width can still carry caching-allocator
+        # growth (one 10.8 ms outlier against 6.0 ms for K = 512, e_dim 128 in an earlier run of this script)
+        best = None
+        for _pass in range(2):
+            _cabi.lib.dvq_profile_enable(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.iters):
+                r = m(z, True)
+            e1.record(); torch.cuda.synchronize(dev)
+            pm, _ = _cabi.profile_mean()
+            _cabi.lib.dvq_profile_enable(0)
+            t = e0.elapsed_time(e1) / args.iters
+            if best is None or t < best[0]:
+                best = (t, pm)
+        ms, prof_ms = best
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64); tdist.all_reduce(t, op=tdist.ReduceOp.MAX); ms = float(t.item())
     refined, err = m.last_counters(N)
