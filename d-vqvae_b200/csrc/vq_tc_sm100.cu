@@ -37,7 +37,9 @@
 // Warp-to-warp hand-offs are hardware named barriers (bar.arrive / bar.sync), mbarriers only where the
 // async proxy signals.  TMEM: 512 columns = 2 accumulator stages of 256, so the MMA of one 256-code
 // chunk overlaps the epilogue of the previous one.  The codebook operand image (K x (D+16) fp16) stays
-// resident in shared memory for K <= 512 and is streamed per row tile above.
+// resident in shared memory for K <= 512 and is streamed per row tile above — by one CTA per SM, or (template
+// parameter PAIR: e_dim 512, e_dim 128 / 256 from K = 2048 on) by CTA pairs that run one M = 256 tcgen05.mma.cta_group::2
+// per k-step over both SMs' row tiles and stream half of every operand block each (see the comment above vq_tc_kernel).
 #include <cuda.h>        // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
 #include <cuda_fp16.h>
 #include <cstddef>
@@ -445,7 +447,8 @@ __device__ __forceinline__ float half_minus_float(uint32_t h16, float a) {
 }
 
 // All barriers live in one shared struct so that a site addresses its barrier as base + immediate.
-// (B_PEER_*: CTA-pair kernel, used in the leader CTA only — the peer CTA's forwarder warp arrives on them remotely)
+// (B_PEER_*: CTA-pair kernel, used in the leader CTA only — the peer CTA arrives on them remotely: its warp 1 once per tile
+// on B_PEER_A_FULL, each of its filter warps once per chunk on B_PEER_ACC_EMPTY)
 enum BarId { B_STAGE_FULL = 0, B_STAGE_EMPTY = 2, B_ACC_FULL = 4, B_A_EMPTY = 6, B_B_FULL = 8, B_B_EMPTY = 8 + MAX_BSLOTS,
              B_PEER_A_FULL = 8 + 2 * MAX_BSLOTS, B_PEER_ACC_EMPTY = 10 + 2 * MAX_BSLOTS, NBARS = 12 + 2 * MAX_BSLOTS };
 // named barrier ids (0 is __syncthreads).  The accumulator-full relay has one barrier per (stage, warp group):
