@@ -480,6 +480,35 @@ def test_streamed_kernel_variants_behind_env_switches(env):
     assert r.returncode == 0 and "VARIANT_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
 
 
+@pytest.mark.parametrize("K,D", [(2048, 128), (1024, 512), (4096, 64)], ids=["cta_pair_d128", "cta_pair_d512", "single_cta_streamed"])
+def test_streamed_kernels_replay_from_a_cuda_graph(K, D):
+    """The streamed kernels — incl. the CTA-pair kernel's cluster launch (cudaLaunchKernelEx) and its per-call tensor maps —
+    are ordinary stream work: a captured inference call replays with new inputs and gives the eager results."""
+    N = 20000 + 37
+    E = vo.default_codebook(K, D, 61)
+    m = _module(E, 1.0, 0.25, 0x20)   # tcgen05 path
+    m.onehot_limit_bytes = 0
+    z_static = torch.from_numpy(vo.normal_latents(N, D, 62)).cuda()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        for _ in range(2):
+            m(z_static, False)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph), torch.no_grad():
+        idx_g, zq_g = m(z_static, False)
+    for seed in (63, 64):
+        z_new = torch.from_numpy(vo.normal_latents(N, D, seed)).cuda()
+        z_static.copy_(z_new)
+        graph.replay()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            idx_e, zq_e = m(z_new, False)
+        assert torch.equal(idx_g, idx_e) and torch.equal(zq_g, zq_e), (K, D, seed)
+    assert m.last_counters(N)[1] == 0
+
+
 def test_backward_kernel_sharded_scale_and_ema_hooks():
     """dvq_vq_backward with a row count that is NOT the local N (the row-sharded case: the loss is a mean over the
     global rows), dvq_vq_code_sums, and the EMA / usage-reset hooks against their torch restatements."""
