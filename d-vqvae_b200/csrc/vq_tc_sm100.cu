@@ -60,7 +60,11 @@ constexpr int A_CHUNK_BYTES = TM * 16 + 32;  // one 8-wide k-chunk of the A imag
 constexpr int BLOAD_WARP = 2;                // codebook streamer (active when the image is not resident)
 constexpr int CONV_WARP0 = 4;
 constexpr int EPI_WARP0 = 8;
+#ifdef DVQ_EPQ4   // experiment: four epilogue warps per lane quarter (28 warps, 72 registers per thread at launch)
+constexpr int EPQ = 4;
+#else
 constexpr int EPQ = 3;                       // epilogue warps per TMEM lane quarter (they split the columns)
+#endif
 constexpr int EPI_WARPS = 4 * EPQ;
 constexpr int GATHER_WARP0 = EPI_WARP0 + EPI_WARPS;
 constexpr int GATHER_WARPS = 4;
@@ -69,7 +73,11 @@ constexpr int NUM_WARPS = GATHER_WARP0 + GATHER_WARPS;
 // group hands 32 per thread back and the gather group takes them: its two batches of 128-bit loads in flight
 // (plus the z rows requested ahead of the codes) do not fit 80.  The trade must balance inside the CTA's own
 // allocation — setmaxnreg.inc only draws from what the CTA released: 128 * (48 + 80 + 112) + 384 * 80 = 61 440.
+#ifdef DVQ_EPQ4   // the launch hands out 896 * 72 = 64 512 registers: 128 * (40 + 72 + 104) + 512 * 72 = 64 512
+constexpr int REGS_CTRL = 40, REGS_GATHER = 104;
+#else
 constexpr int REGS_CTRL = 48, REGS_GATHER = 112;
+#endif
 // streamed-codebook variant (ST): control 40, converter 64, gather 64, epilogue 104 (128 * (40 + 64 + 64) + 384 * 104 = 61 440)
 constexpr int REGS_ST_CTRL = 40, REGS_ST_SIDE = 64, REGS_ST_EPI = 104;
 constexpr int DSLICE = 64;                   // e_dim is contracted in slices of at most 64 columns
