@@ -129,6 +129,11 @@ int dvq_debug_tc_pair_layout(long long N, int K, int D, int* out8) {
   return DVQ_OK;
 }
 
+long long dvq_debug_tc_image_offset(int k, int d, int K, int D, int pair, long long* image_bytes) {
+  if (K <= 0 || D <= 0 || k < 0 || k >= K || d < 0 || d >= D + 16 || !vq_tc_supported(1, K, D)) return -1;
+  return vq_tc_image_offset(k, d, K, D, pair, image_bytes);
+}
+
 int dvq_profile_enable(int on) {
   g_prof_on = on != 0;
   for (int i = 0; i < kStages; ++i) g_prof_n[i] = 0;

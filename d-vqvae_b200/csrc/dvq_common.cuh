@@ -61,6 +61,7 @@ bool vq_tc_supported(int64_t N, int K, int D);
 void vq_tc_layout_info(int K, int D, int* out8);   // dvq_debug_tc_layout
 bool vq_tc_pair_selected(int64_t N, int K, int D);   // CTA-pair (cta_group::2) kernel for this shape?
 void vq_tc_pair_layout_info(int64_t N, int K, int D, int* out8);   // dvq_debug_tc_pair_layout
+long long vq_tc_image_offset(int k, int d, int K, int D, int pair, long long* image_bytes);   // dvq_debug_tc_image_offset
 size_t vq_tc_operand_bytes(int K, int D);
 int launch_vq_tc(const float* z, const float* E, const float* ee, int64_t N, int K, int D, int train,
                  float* z_q, int64_t* idx, unsigned long long* hist, double* sse,

@@ -1507,6 +1507,14 @@ bool vq_tc_supported(int64_t N, int K, int D) {
   return smem_layout(K, D).total <= SMEM_LIMIT;
 }
 
+// dvq_debug_tc_image_offset: byte offset of (code k, column d; d in [D, D + 16) = fold columns) in the global operand image of
+// either layout, and the image size (host-only; tests/test_cabi_symbols.py checks that the maps are injective and in range)
+long long vq_tc_image_offset(int k, int d, int K, int D, int pair, long long* image_bytes) {
+  const SmemLayout L1 = smem_layout(K, D);
+  if (image_bytes) *image_bytes = (long long)((K + 255) / 256) * L1.ns * L1.bchunk_bytes;
+  return (long long)bimg_offset(k, d, D, K, pair != 0);
+}
+
 // CTA-pair kernel (cta_group::2) for this call?  Streamed codebooks only.  Measured at N = 16.8M against the single-CTA
 // kernel, whole call (profiles/README.md): e_dim 512 1.05x (K = 512) .. 1.67x (K = 16 384); e_dim 256 1.11-1.27x from
 // K = 2048 on, 0.93x at K = 1024; e_dim 128 1.06-1.09x from K = 2048 on, 0.91x at K = 512; e_dim 64 0.98-1.00x (one slice

@@ -37,6 +37,7 @@ SYMBOLS = {
     "dvq_vq_set_refine": (_i, [_i, C.c_longlong]),
     "dvq_debug_tc_layout": (_i, [_i, _i, C.POINTER(_i)]),
     "dvq_debug_tc_pair_layout": (_i, [C.c_longlong, _i, _i, C.POINTER(_i)]),
+    "dvq_debug_tc_image_offset": (C.c_longlong, [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)]),
     "dvq_profile_mean": (_i, [C.POINTER(_f), C.POINTER(_i), _i]),
     "dvq_debug_umma": (_i, [_vp, C.c_uint32, _vp, C.c_uint32, _i, C.POINTER(C.c_uint32), C.c_uint32, _i, _vp, _vp, _vp]),
     "dvq_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),

@@ -93,6 +93,12 @@ DVQ_API int dvq_debug_tc_layout(int K, int D, int* out8);
  * shared memory in bytes, codes per ring slot (128) } of the pair kernel's plan. */
 DVQ_API int dvq_debug_tc_pair_layout(long long N, int K, int D, int* out8);
 
+/* Diagnostic (host-only): byte offset of element (code k, column d) of the FP16 operand image the tcgen05 VQ kernel keeps in
+ * its workspace — d in [0, D) the scaled code, d in [D, D + 16) the fold columns — for the single-CTA layout (pair = 0: blocks
+ * of 256 codes) or the CTA-pair layout (pair = 1: half blocks of 128-code capacity, lower / upper half of a chunk's codes),
+ * and the image size in *image_bytes (may be NULL).  -1 for an unsupported shape or an index out of range. */
+DVQ_API long long dvq_debug_tc_image_offset(int k, int d, int K, int D, int pair, long long* image_bytes);
+
 /* Diagnostic used by tests/test_tc_probe_gpu.py: run `ksteps` tcgen05.mma (M=128, N=n_cols,
  * kind::f16) on caller-built shared-memory operand images and dump the [128,n_cols] fp32
  * accumulator.  strides = {a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep} in bytes; *err (device

@@ -169,6 +169,36 @@ def test_tc_pair_kernel_selection_rule():
     assert plan(N, 128, 256)["pair"] == 0             # the grasp codebooks (K = 128): single-CTA kernel
 
 
+@pytest.mark.parametrize("K,D", [(512, 64), (544, 128), (1024, 256), (288, 512)])
+def test_tc_operand_image_maps_are_injective(K, D):
+    """Host-only: both layouts of the FP16 operand image (single CTA: 256-code blocks; CTA pair: half blocks, the lower /
+    upper half of a chunk's codes for CTA 0 / 1) map every (code, column incl. the 16 fold columns) to its own 2-byte
+    slot inside the image; in the pair layout the two halves of a chunk lie in different half blocks and a half block's
+    codes are contiguous 16-byte rows per 8-column group (the K-major core-matrix rows the UMMA descriptor walks)."""
+    from dvq import _cabi
+    size = ctypes.c_longlong()
+    for pair in (0, 1):
+        seen = set()
+        for k in range(K):
+            for d in range(0, D + 16):
+                off = _cabi.lib.dvq_debug_tc_image_offset(k, d, K, D, pair, ctypes.byref(size))
+                assert 0 <= off and off + 2 <= size.value and off % 2 == 0, (pair, k, d, off, size.value)
+                assert off not in seen, (pair, k, d)
+                seen.add(off)
+    off = lambda k, d, pair: _cabi.lib.dvq_debug_tc_image_offset(k, d, K, D, pair, None)
+    # 8 consecutive columns of a code are one 16-byte row; the next code of the same half follows 16 bytes later
+    assert [off(0, d, 1) - off(0, 0, 1) for d in range(8)] == [0, 2, 4, 6, 8, 10, 12, 14]
+    assert off(1, 0, 1) - off(0, 0, 1) == 16 and off(1, 0, 0) - off(0, 0, 0) == 16
+    # the last chunk's codes split in two halves (ragged K: half of what is left), each inside its own half block
+    last = (K - 1) // 256 * 256
+    nh = (min(256, K - last)) // 2
+    ds = D if D <= 64 else (64 if D <= 256 else 32)
+    half_bytes = (ds // 8 + 2) * 128 * 16
+    assert off(last + nh, 0, 1) // half_bytes == off(last, 0, 1) // half_bytes + 1
+    assert off(last + nh - 1, 0, 1) // half_bytes == off(last, 0, 1) // half_bytes
+    assert _cabi.lib.dvq_debug_tc_image_offset(K, 0, K, D, 0, None) == -1
+
+
 def test_module_caches_survive_deepcopy_and_see_reloaded_weights():
     """cached device-pointer structs made the modules unpicklable, and the fold / pack caches could go
     stale.  CPU-only checks of the host logic: deepcopy / pickle work, load_state_dict invalidates the caches."""
